@@ -1,0 +1,870 @@
+// altro_abi.cu -- C ABI (include/altro_b200.h) over the sm_100a batched ALTRO kernels.
+//
+// Owns the device-resident problem batch (dynamics, weights, references, constraint data,
+// trajectories, duals, per-instance statistics) of one handle and launches the solve /
+// shift / MPC-transition kernels on the handle's stream.  No CPU fallback anywhere: every
+// compute entry point fails with ALTRO_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "altro_kernels.cuh"
+
+using namespace altro;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct HostCon {
+    int sense, side, k0, k1, p, w, per_knot, per_instance, rowsparse;
+    std::vector<int> inds, rs_col;
+    std::vector<double> rs_coef;
+    double *G_dev = nullptr, *h_dev = nullptr, *rs_coef_dev = nullptr;
+    int *rs_col_dev = nullptr;
+    size_t g_count = 0, h_count = 0;
+};
+
+}  // namespace
+
+struct altro_handle_s {
+    int device = 0, n = 0, m = 0, N = 0, B = 0;
+    double dt = 0.0;
+    altro_opts_t opts;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    // dynamics
+    int dyn_per_knot = 0, dyn_per_instance = 0;
+    double *A = nullptr, *Bm = nullptr, *d = nullptr;
+    size_t dyn_count = 0;
+    // cost / reference / state
+    double *Q = nullptr, *R = nullptr, *Qf = nullptr, *xref = nullptr, *uref = nullptr, *x0 = nullptr;
+    double *X = nullptr, *U = nullptr, *lam = nullptr;
+    double *X_snap = nullptr, *U_snap = nullptr, *lam_snap = nullptr;
+    // stats
+    int *iters = nullptr, *outer = nullptr, *status = nullptr, *trials = nullptr;
+    double *cost = nullptr, *cost_al = nullptr, *cmax = nullptr, *penmax = nullptr;
+    long long *t_ns = nullptr;
+    double *trace = nullptr;
+    int trace_rows = 0;
+    // constraints
+    std::vector<HostCon> cons;
+    ConDesc *con_dev = nullptr;
+    int P = 0, EX = 0;
+    bool finalized = false, have_dyn = false, have_cost = false, have_ref = false, have_x0 = false;
+    // MPC track
+    double *trackX = nullptr, *trackU = nullptr, *noise = nullptr;
+    int *kidx = nullptr;
+    int Nt = 0;
+    // launch
+    int threads_req = 0, threads = 0, smem = 0, regs = 0, ctas_per_sm = 0, num_sms = 0, dyn_in_smem = 0, ref_in_smem = 1;
+    const void *kernel = nullptr;
+};
+
+namespace {
+
+int fail(altro_handle_t h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+
+#define CK(h, call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(h, ALTRO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+template <typename Tp>
+cudaError_t dalloc(Tp **p, size_t count)
+{
+    cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(Tp));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(Tp));
+    return e;
+}
+
+// ------------------------------------------------------------------ auxiliary kernels
+
+// RD.shift_fill!(Z) / Altro.shift_fill!(conSet): z_k <- z_{k+1}, last knot kept. One CTA per instance.
+__global__ void shift_fill_kernel(int n, int m, int N, int P, int ncon, const ConDesc *con, double *X, double *U,
+                                  double *lam, int primal, int dual)
+{
+    extern __shared__ double buf[];
+    const int inst = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    if (primal) {
+        double *x = X + (size_t)inst * N * n, *u = U + (size_t)inst * (N - 1) * m;
+        for (int i = tid; i < (N - 1) * n; i += T) buf[i] = x[i + n];
+        __syncthreads();
+        for (int i = tid; i < (N - 1) * n; i += T) x[i] = buf[i];
+        __syncthreads();
+        for (int i = tid; i < (N - 2) * m; i += T) buf[i] = u[i + m];
+        __syncthreads();
+        for (int i = tid; i < (N - 2) * m; i += T) u[i] = buf[i];
+        __syncthreads();
+    }
+    if (dual) {
+        double *l = lam + (size_t)inst * P;
+        for (int i = tid; i < P; i += T) buf[i] = l[i];
+        __syncthreads();
+        for (int c = 0; c < ncon; ++c) {
+            const int nk = con[c].k1 - con[c].k0, p = con[c].p, off = con[c].dual_off;
+            for (int i = tid; i < (nk - 1) * p; i += T) l[off + i] = buf[off + i + p];
+        }
+    }
+}
+
+// Device-side MPC transition (random_linear_problem.jl:121-139, simple_rocket.jl:59-82):
+// plant step with the first control (+ noise), reference window advanced along the track.
+__global__ void mpc_transition_kernel(int n, int m, int N, const double *A, const double *Bm, const double *d,
+                                      int dyn_per_knot, int dyn_per_instance, const double *X, const double *U,
+                                      const double *noise, double *x0, const double *trackX, const double *trackU,
+                                      int Nt, int *kidx, double *xref, double *uref)
+{
+    const int inst = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const size_t base = dyn_per_instance ? (size_t)inst * (dyn_per_knot ? (size_t)(N - 1) : 1) : 0;
+    const double *A0 = A + base * n * n, *B0 = Bm + base * n * m, *d0 = d + base * n;
+    const double *x = X + (size_t)inst * N * n, *u = U + (size_t)inst * (N - 1) * m;
+    for (int i = tid; i < n; i += T) {
+        double acc = d0[i];
+        for (int j = 0; j < n; ++j) acc = fma(A0[i * n + j], x[j], acc);
+        for (int j = 0; j < m; ++j) acc = fma(B0[i * m + j], u[j], acc);
+        if (noise) acc += noise[(size_t)inst * n + i];
+        x0[(size_t)inst * n + i] = acc;
+    }
+    if (trackX) {
+        const int k0 = kidx[inst] + 1;
+        __syncthreads();
+        if (tid == 0) kidx[inst] = k0;
+        double *xr = xref + (size_t)inst * N * n, *ur = uref + (size_t)inst * (N - 1) * m;
+        for (int i = tid; i < N * n; i += T) {
+            int k = min(k0 + i / n, Nt - 1);
+            xr[i] = trackX[(size_t)k * n + i % n];
+        }
+        for (int i = tid; i < (N - 1) * m; i += T) {
+            int k = min(k0 + i / m, Nt - 2);
+            ur[i] = trackU[(size_t)k * m + i % m];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ FP64 peak microbenchmarks
+
+__global__ void dfma_peak_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void dmma_peak_kernel(double *out, int iters)
+{
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+    for (int i = 0; i < iters; ++i) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c2), "+d"(c3) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c4), "+d"(c5) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c6), "+d"(c7) : "d"(a), "d"(b));
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+}
+
+// ------------------------------------------------------------------ kernel dispatch
+
+}  // namespace
+
+namespace altro {
+// one translation unit per compiled dimension pair (inst_*.cu)
+const void *kernel_6_3(int T);    // rocket
+const void *kernel_12_12(int T);  // quadruped
+const void *kernel_6_6(int T);    // grasp
+const void *kernel_12_3(int T);   // flexible satellite
+const void *kernel_12_6(int T);   // random linear (default)
+const void *kernel_0_0(int T);    // run-time dimensions
+}  // namespace altro
+
+namespace {
+
+const void *find_kernel(int n, int m, int T)
+{
+    if (getenv("ALTRO_B200_GENERIC")) return kernel_0_0(T);
+    if (n == 6 && m == 3) return kernel_6_3(T);
+    if (n == 12 && m == 12) return kernel_12_12(T);
+    if (n == 6 && m == 6) return kernel_6_6(T);
+    if (n == 12 && m == 3) return kernel_12_3(T);
+    if (n == 12 && m == 6) return kernel_12_6(T);
+    return kernel_0_0(T);
+}
+
+int finalize(altro_handle_t h)
+{
+    if (h->finalized) return ALTRO_OK;
+    if (!h->have_dyn || !h->have_cost) return fail(h, ALTRO_ERR_STATE, "dynamics and cost must be set before solve");
+    const int n = h->n, m = h->m, N = h->N, B = h->B;
+    // dual / expansion offsets, device descriptors
+    std::vector<ConDesc> cd(std::max<size_t>(h->cons.size(), 1));
+    int P = 0, EX = 0;
+    for (size_t i = 0; i < h->cons.size(); ++i) {
+        HostCon &c = h->cons[i];
+        ConDesc &dsc = cd[i];
+        memset(&dsc, 0, sizeof(dsc));
+        dsc.sense = c.sense; dsc.side = c.side; dsc.k0 = c.k0; dsc.k1 = c.k1; dsc.p = c.p; dsc.w = c.w;
+        dsc.per_knot = c.per_knot; dsc.per_instance = c.per_instance; dsc.rowsparse = c.rowsparse;
+        dsc.dual_off = P;
+        dsc.ex_off = EX;
+        dsc.ex_stride = c.rowsparse ? 2 * c.w : c.w + c.w * c.w;
+        dsc.G = c.G_dev; dsc.h = c.h_dev; dsc.rs_col = c.rs_col_dev; dsc.rs_coef = c.rs_coef_dev;
+        for (int j = 0; j < c.w; ++j) dsc.inds[j] = c.inds[j];
+        P += (c.k1 - c.k0) * c.p;
+        EX += (c.k1 - c.k0) * dsc.ex_stride;
+    }
+    h->P = P;
+    h->EX = EX;
+    CK(h, dalloc(&h->con_dev, cd.size()));
+    CK(h, cudaMemcpy(h->con_dev, cd.data(), cd.size() * sizeof(ConDesc), cudaMemcpyHostToDevice));
+    CK(h, dalloc(&h->lam, (size_t)B * P));
+    CK(h, dalloc(&h->lam_snap, (size_t)B * P));
+    // launch geometry
+    cudaDeviceProp prop;
+    CK(h, cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    const int maxdim = std::max(n, m);
+    int T = h->threads_req;
+    if (const char *e = getenv("ALTRO_B200_THREADS")) T = atoi(e);
+    if (T == 0) T = maxdim <= 8 ? 32 : maxdim <= 16 ? 64 : maxdim <= 32 ? 128 : 256;
+    if (T != 32 && T != 64 && T != 128 && T != 256) return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 32, 64, 128 or 256");
+    h->threads = T;
+    h->dyn_in_smem = (!h->dyn_per_knot && !h->dyn_per_instance) ? 1 : 0;
+    h->ref_in_smem = 1;
+    size_t smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 1, T);
+    if (smem > (size_t)prop.sharedMemPerBlockOptin) {  // long horizons: keep the reference in global memory
+        h->ref_in_smem = 0;
+        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 0, T);
+    }
+    if (smem > (size_t)prop.sharedMemPerBlockOptin && h->dyn_in_smem) {
+        h->dyn_in_smem = 0;
+        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, 0, 0, T);
+    }
+    if (smem > (size_t)prop.sharedMemPerBlockOptin) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "problem needs %zu B of shared memory per instance, device offers %zu B "
+                 "(n=%d m=%d N=%d P=%d): not supported by the shared-memory-resident kernel", smem,
+                 (size_t)prop.sharedMemPerBlockOptin, n, m, N, P);
+        return fail(h, ALTRO_ERR_UNSUPPORTED, buf);
+    }
+    h->smem = (int)smem;
+    h->kernel = find_kernel(n, m, T);
+    if (!h->kernel) return fail(h, ALTRO_ERR_UNSUPPORTED, "no kernel for this configuration");
+    CK(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    CK(h, cudaFuncGetAttributes(&fa, h->kernel));
+    h->regs = fa.numRegs;
+    int nb = 0;
+    CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, h->kernel, T, smem));
+    h->ctas_per_sm = nb;
+    h->finalized = true;
+    return ALTRO_OK;
+}
+
+int upload(altro_handle_t h, double *dst, const double *src, size_t count)
+{
+    CK(h, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return ALTRO_OK;
+}
+
+int download(altro_handle_t h, void *dst, const void *src, size_t bytes)
+{
+    CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return ALTRO_OK;
+}
+
+}  // namespace
+
+#define REQ(h)                                                       \
+    do {                                                             \
+        if (!(h)) return fail(nullptr, ALTRO_ERR_INVALID, "null handle"); \
+        cudaError_t e_ = cudaSetDevice((h)->device);                 \
+        if (e_ != cudaSuccess) return fail(h, ALTRO_ERR_CUDA, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" {
+
+int altro_default_options(altro_opts_t *o)
+{
+    if (!o) return ALTRO_ERR_INVALID;
+    o->constraint_tolerance = 1e-6;
+    o->cost_tolerance = 1e-4;
+    o->cost_tolerance_intermediate = 1e-4;
+    o->gradient_tolerance = 10.0;
+    o->gradient_tolerance_intermediate = 1.0;
+    o->penalty_initial = 1.0;
+    o->penalty_scaling = 10.0;
+    o->penalty_max = 1e8;
+    o->dual_max = 1e8;
+    o->line_search_lower_bound = 1e-8;
+    o->line_search_upper_bound = 10.0;
+    o->max_cost_value = 1e8;
+    o->max_state_value = 1e8;
+    o->bp_reg_initial = 0.0;
+    o->bp_reg_increase_factor = 1.6;
+    o->bp_reg_max = 1e8;
+    o->bp_reg_min = 1e-8;
+    o->bp_reg_fp = 10.0;
+    o->iterations = 1000;
+    o->iterations_inner = 300;
+    o->iterations_outer = 30;
+    o->iterations_linesearch = 20;
+    o->dJ_counter_limit = 10;
+    o->reset_duals = 1;
+    o->reset_penalties = 1;
+    o->kickout_max_penalty = 0;
+    o->dj_zero_converges = 1;
+    o->soc_hess_exact = 1;
+    o->soc_viol_proj = 1;
+    return ALTRO_OK;
+}
+
+const char *altro_last_error(altro_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int altro_create(altro_handle_t *out, int device, int n, int m, int N, int batch, double dt)
+{
+    if (!out || n < 1 || m < 1 || N < 2 || batch < 1) return fail(nullptr, ALTRO_ERR_INVALID, "bad dimensions");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, ALTRO_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") +
+                                                 cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, ALTRO_ERR_INVALID, "bad device index");
+    altro_handle_t h = new altro_handle_s();
+    h->device = device; h->n = n; h->m = m; h->N = N; h->B = batch; h->dt = dt;
+    altro_default_options(&h->opts);
+#define CKC(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e2_ = (call);                                                              \
+        if (e2_ != cudaSuccess) {                                                              \
+            fail(nullptr, ALTRO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e2_)); \
+            altro_destroy(h);                                                                  \
+            return ALTRO_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&h->ev0));
+    CKC(cudaEventCreate(&h->ev1));
+    const size_t B = batch;
+    CKC(dalloc(&h->Q, n)); CKC(dalloc(&h->R, m)); CKC(dalloc(&h->Qf, n));
+    CKC(dalloc(&h->xref, B * N * n)); CKC(dalloc(&h->uref, B * (N - 1) * m)); CKC(dalloc(&h->x0, B * n));
+    CKC(dalloc(&h->X, B * N * n)); CKC(dalloc(&h->U, B * (N - 1) * m));
+    CKC(dalloc(&h->X_snap, B * N * n)); CKC(dalloc(&h->U_snap, B * (N - 1) * m));
+    CKC(dalloc(&h->iters, B)); CKC(dalloc(&h->outer, B)); CKC(dalloc(&h->status, B)); CKC(dalloc(&h->trials, B));
+    CKC(dalloc(&h->cost, B)); CKC(dalloc(&h->cost_al, B)); CKC(dalloc(&h->cmax, B)); CKC(dalloc(&h->penmax, B));
+    CKC(dalloc(&h->t_ns, B)); CKC(dalloc(&h->noise, B * n)); CKC(dalloc(&h->kidx, B));
+#undef CKC
+    *out = h;
+    return ALTRO_OK;
+}
+
+int altro_destroy(altro_handle_t h)
+{
+    if (!h) return ALTRO_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
+                    h->U_snap, h->lam_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
+                    h->penmax, h->t_ns, h->trace, h->con_dev, h->trackX, h->trackU, h->noise, h->kidx};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (auto &c : h->cons) {
+        if (c.G_dev) cudaFree(c.G_dev);
+        if (c.h_dev) cudaFree(c.h_dev);
+        if (c.rs_col_dev) cudaFree(c.rs_col_dev);
+        if (c.rs_coef_dev) cudaFree(c.rs_coef_dev);
+    }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ALTRO_OK;
+}
+
+int altro_set_stream(altro_handle_t h, void *s)
+{
+    REQ(h);
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)s;
+    h->own_stream = false;
+    return ALTRO_OK;
+}
+
+int altro_set_options(altro_handle_t h, const altro_opts_t *o)
+{
+    REQ(h);
+    if (!o) return fail(h, ALTRO_ERR_INVALID, "null options");
+    if (o->iterations_outer < 1 || o->iterations_inner < 1 || !(o->penalty_initial > 0.0))
+        return fail(h, ALTRO_ERR_INVALID, "bad option values");
+    h->opts = *o;
+    return ALTRO_OK;
+}
+
+int altro_set_dynamics(altro_handle_t h, int per_knot, int per_instance, const double *A, const double *Bm,
+                       const double *d)
+{
+    REQ(h);
+    if (!A || !Bm) return fail(h, ALTRO_ERR_INVALID, "null dynamics");
+    const size_t cnt = (per_instance ? (size_t)h->B : 1) * (per_knot ? (size_t)(h->N - 1) : 1);
+    if (h->have_dyn && (cnt != h->dyn_count || per_knot != h->dyn_per_knot || per_instance != h->dyn_per_instance)) {
+        if (h->finalized) return fail(h, ALTRO_ERR_STATE, "dynamics layout cannot change after the first solve");
+        cudaFree(h->A); cudaFree(h->Bm); cudaFree(h->d);
+        h->A = h->Bm = h->d = nullptr;
+        h->have_dyn = false;
+    }
+    const size_t n = h->n, m = h->m;
+    if (!h->have_dyn) {
+        CK(h, dalloc(&h->A, cnt * n * n));
+        CK(h, dalloc(&h->Bm, cnt * n * m));
+        CK(h, dalloc(&h->d, cnt * n));
+        h->dyn_count = cnt; h->dyn_per_knot = per_knot; h->dyn_per_instance = per_instance;
+        h->have_dyn = true;
+    }
+    int rc = upload(h, h->A, A, cnt * n * n);
+    if (rc) return rc;
+    rc = upload(h, h->Bm, Bm, cnt * n * m);
+    if (rc) return rc;
+    if (d) return upload(h, h->d, d, cnt * n);
+    CK(h, cudaMemsetAsync(h->d, 0, cnt * n * sizeof(double), h->stream));
+    return ALTRO_OK;
+}
+
+int altro_set_cost_diag(altro_handle_t h, const double *Q, const double *R, const double *Qf)
+{
+    REQ(h);
+    if (!Q || !R || !Qf) return fail(h, ALTRO_ERR_INVALID, "null weights");
+    for (int i = 0; i < h->m; ++i)
+        if (!(R[i] > 0.0)) return fail(h, ALTRO_ERR_INVALID, "R must be positive");
+    int rc = upload(h, h->Q, Q, h->n);
+    if (!rc) rc = upload(h, h->R, R, h->m);
+    if (!rc) rc = upload(h, h->Qf, Qf, h->n);
+    // the three vectors are tiny and caller-owned: make sure they are consumed before returning
+    if (!rc) CK(h, cudaStreamSynchronize(h->stream));
+    h->have_cost = true;
+    return rc;
+}
+
+int altro_set_reference(altro_handle_t h, const double *Xref, const double *Uref)
+{
+    REQ(h);
+    int rc = ALTRO_OK;
+    if (Xref) rc = upload(h, h->xref, Xref, (size_t)h->B * h->N * h->n);
+    if (!rc && Uref) rc = upload(h, h->uref, Uref, (size_t)h->B * (h->N - 1) * h->m);
+    h->have_ref = true;
+    return rc;
+}
+
+int altro_add_constraint(altro_handle_t h, int sense, int side, int k0, int k1, int p, int w, const int *inds,
+                         int per_knot, int per_instance, const double *G, const double *hv, int *con_id)
+{
+    REQ(h);
+    if (h->finalized) return fail(h, ALTRO_ERR_STATE, "constraints must be added before the first solve");
+    if ((int)h->cons.size() >= MAX_CON) return fail(h, ALTRO_ERR_UNSUPPORTED, "too many constraint blocks");
+    if (sense < 0 || sense > 2 || side < 0 || side > 1 || !inds || !G || !hv || p < 1 || w < 1)
+        return fail(h, ALTRO_ERR_INVALID, "bad constraint arguments");
+    const int kmax = side == ALTRO_CONTROL ? h->N - 1 : h->N;
+    if (k0 < 0 || k1 > kmax || k1 <= k0) return fail(h, ALTRO_ERR_INVALID, "bad knot range (control blocks end at N-1)");
+    if (w > MAX_W) return fail(h, ALTRO_ERR_UNSUPPORTED, "constraint index set wider than 32");
+    const int lim = side == ALTRO_CONTROL ? h->m : h->n;
+    for (int j = 0; j < w; ++j)
+        if (inds[j] < 0 || inds[j] >= lim) return fail(h, ALTRO_ERR_INVALID, "constraint index out of range");
+    if (sense == ALTRO_SECOND_ORDER_CONE && p < 2) return fail(h, ALTRO_ERR_INVALID, "a cone block needs >= 2 rows");
+    HostCon c;
+    c.sense = sense; c.side = side; c.k0 = k0; c.k1 = k1; c.p = p; c.w = w;
+    c.per_knot = per_knot; c.per_instance = per_instance;
+    c.inds.assign(inds, inds + w);
+    const size_t cnt = (per_instance ? (size_t)h->B : 1) * (per_knot ? (size_t)(k1 - k0) : 1);
+    c.g_count = cnt * p * w;
+    c.h_count = cnt * p;
+    // row-sparse detection (bounds): shared data, not a cone, every row has at most one nonzero
+    c.rowsparse = 0;
+    if (!per_knot && !per_instance && sense != ALTRO_SECOND_ORDER_CONE) {
+        bool rs = true;
+        std::vector<int> col(p, 0);
+        std::vector<double> coef(p, 0.0);
+        for (int r = 0; r < p && rs; ++r) {
+            int nz = 0;
+            for (int j = 0; j < w; ++j)
+                if (G[r * w + j] != 0.0) { ++nz; col[r] = j; coef[r] = G[r * w + j]; }
+            rs = nz <= 1;
+        }
+        if (rs) { c.rowsparse = 1; c.rs_col = col; c.rs_coef = coef; }
+    }
+    if (!c.rowsparse && p > PMAX) return fail(h, ALTRO_ERR_UNSUPPORTED, "dense constraint block with more than 16 rows");
+    CK(h, dalloc(&c.G_dev, c.g_count));
+    CK(h, dalloc(&c.h_dev, c.h_count));
+    CK(h, cudaMemcpy(c.G_dev, G, c.g_count * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(c.h_dev, hv, c.h_count * sizeof(double), cudaMemcpyHostToDevice));
+    if (c.rowsparse) {
+        CK(h, dalloc(&c.rs_col_dev, p));
+        CK(h, dalloc(&c.rs_coef_dev, p));
+        CK(h, cudaMemcpy(c.rs_col_dev, c.rs_col.data(), p * sizeof(int), cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(c.rs_coef_dev, c.rs_coef.data(), p * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->cons.push_back(c);
+    if (con_id) *con_id = (int)h->cons.size() - 1;
+    return ALTRO_OK;
+}
+
+int altro_update_constraint_data(altro_handle_t h, int id, const double *G, const double *hv)
+{
+    REQ(h);
+    if (id < 0 || id >= (int)h->cons.size()) return fail(h, ALTRO_ERR_INVALID, "bad constraint id");
+    HostCon &c = h->cons[id];
+    if (c.rowsparse && G) return fail(h, ALTRO_ERR_UNSUPPORTED, "G of a row-sparse (bound) block is fixed; update h only");
+    int rc = ALTRO_OK;
+    if (G) rc = upload(h, c.G_dev, G, c.g_count);
+    if (!rc && hv) rc = upload(h, c.h_dev, hv, c.h_count);
+    return rc;
+}
+
+int altro_set_x0(altro_handle_t h, const double *x0)
+{
+    REQ(h);
+    if (!x0) return fail(h, ALTRO_ERR_INVALID, "null x0");
+    h->have_x0 = true;
+    return upload(h, h->x0, x0, (size_t)h->B * h->n);
+}
+
+int altro_set_trajectory(altro_handle_t h, const double *X, const double *U)
+{
+    REQ(h);
+    int rc = ALTRO_OK;
+    if (X) rc = upload(h, h->X, X, (size_t)h->B * h->N * h->n);
+    if (!rc && U) rc = upload(h, h->U, U, (size_t)h->B * (h->N - 1) * h->m);
+    return rc;
+}
+
+int altro_get_trajectory(altro_handle_t h, double *X, double *U)
+{
+    REQ(h);
+    int rc = ALTRO_OK;
+    if (X) rc = download(h, X, h->X, (size_t)h->B * h->N * h->n * sizeof(double));
+    if (!rc && U) rc = download(h, U, h->U, (size_t)h->B * (h->N - 1) * h->m * sizeof(double));
+    if (!rc) CK(h, cudaStreamSynchronize(h->stream));
+    return rc;
+}
+
+int altro_dual_len(altro_handle_t h, int *P)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (P) *P = h->P;
+    return ALTRO_OK;
+}
+
+int altro_set_duals(altro_handle_t h, const double *lam)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    return upload(h, h->lam, lam, (size_t)h->B * h->P);
+}
+
+int altro_get_duals(altro_handle_t h, double *lam)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    rc = download(h, lam, h->lam, (size_t)h->B * h->P * sizeof(double));
+    if (!rc) CK(h, cudaStreamSynchronize(h->stream));
+    return rc;
+}
+
+int altro_shift_fill(altro_handle_t h, int primal, int dual)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    const size_t words = std::max<size_t>({(size_t)h->N * h->n, (size_t)h->N * h->m, (size_t)h->P, 1});
+    if (words * sizeof(double) > 48 * 1024)
+        CK(h, cudaFuncSetAttribute(shift_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(words * sizeof(double))));
+    shift_fill_kernel<<<h->B, 128, words * sizeof(double), h->stream>>>(h->n, h->m, h->N, h->P, (int)h->cons.size(),
+                                                                      h->con_dev, h->X, h->U, h->lam, primal, dual);
+    CK(h, cudaGetLastError());
+    return ALTRO_OK;
+}
+
+int altro_solve(altro_handle_t h)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (!h->have_x0) return fail(h, ALTRO_ERR_STATE, "x0 not set");
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.n = h->n; P.m = h->m; P.N = h->N; P.B = h->B; P.P = h->P; P.ncon = (int)h->cons.size(); P.EX = h->EX;
+    P.inst_offset = 0;
+    P.dt = h->dt;
+    P.dyn_per_knot = h->dyn_per_knot; P.dyn_per_instance = h->dyn_per_instance; P.dyn_in_smem = h->dyn_in_smem; P.ref_in_smem = h->ref_in_smem;
+    P.A = h->A; P.Bm = h->Bm; P.d = h->d;
+    P.Q = h->Q; P.R = h->R; P.Qf = h->Qf;
+    P.xref = h->xref; P.uref = h->uref; P.x0 = h->x0;
+    P.X = h->X; P.U = h->U; P.lam = h->lam;
+    P.iters = h->iters; P.outer = h->outer; P.status = h->status; P.trials = h->trials;
+    P.cost = h->cost; P.cost_al = h->cost_al; P.cmax = h->cmax; P.penmax = h->penmax;
+    P.t_ns = h->t_ns;
+    P.trace = h->trace;
+    P.trace_rows = h->trace_rows;
+    P.con = h->con_dev;
+    P.o = h->opts;
+    void *args[] = {&P};
+    if (h->trace)
+        CK(h, cudaMemsetAsync(h->trace, 0, (size_t)h->B * h->trace_rows * TRACE_COLS * sizeof(double), h->stream));
+    CK(h, cudaEventRecord(h->ev0, h->stream));
+    CK(h, cudaLaunchKernel(h->kernel, dim3(h->B), dim3(h->threads), args, (size_t)h->smem, h->stream));
+    CK(h, cudaEventRecord(h->ev1, h->stream));
+    return ALTRO_OK;
+}
+
+int altro_sync(altro_handle_t h)
+{
+    REQ(h);
+    CK(h, cudaStreamSynchronize(h->stream));
+    return ALTRO_OK;
+}
+
+int altro_get_stats(altro_handle_t h, int *iterations, int *iterations_outer, int *status, int *ls_trials,
+                    double *cost, double *cost_al, double *c_max, double *penalty_max)
+{
+    REQ(h);
+    const size_t B = h->B;
+    int rc = ALTRO_OK;
+    if (iterations) rc |= download(h, iterations, h->iters, B * sizeof(int));
+    if (iterations_outer) rc |= download(h, iterations_outer, h->outer, B * sizeof(int));
+    if (status) rc |= download(h, status, h->status, B * sizeof(int));
+    if (ls_trials) rc |= download(h, ls_trials, h->trials, B * sizeof(int));
+    if (cost) rc |= download(h, cost, h->cost, B * sizeof(double));
+    if (cost_al) rc |= download(h, cost_al, h->cost_al, B * sizeof(double));
+    if (c_max) rc |= download(h, c_max, h->cmax, B * sizeof(double));
+    if (penalty_max) rc |= download(h, penalty_max, h->penmax, B * sizeof(double));
+    if (rc) return ALTRO_ERR_CUDA;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return ALTRO_OK;
+}
+
+int altro_get_timing(altro_handle_t h, double *device_ms, long long *per_instance_ns)
+{
+    REQ(h);
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (device_ms) {
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *device_ms = ms;
+    }
+    if (per_instance_ns) {
+        int rc = download(h, per_instance_ns, h->t_ns, (size_t)h->B * sizeof(long long));
+        if (rc) return rc;
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    return ALTRO_OK;
+}
+
+int altro_set_trace(altro_handle_t h, int max_rows)
+{
+    REQ(h);
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->trace) { cudaFree(h->trace); h->trace = nullptr; }
+    h->trace_rows = 0;
+    if (max_rows > 0) {
+        CK(h, dalloc(&h->trace, (size_t)h->B * max_rows * TRACE_COLS));
+        h->trace_rows = max_rows;
+    }
+    return ALTRO_OK;
+}
+
+int altro_get_trace(altro_handle_t h, double *out)
+{
+    REQ(h);
+    if (!h->trace || !out) return fail(h, ALTRO_ERR_STATE, "tracing is not enabled");
+    int rc = download(h, out, h->trace, (size_t)h->B * h->trace_rows * TRACE_COLS * sizeof(double));
+    if (rc) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return ALTRO_OK;
+}
+
+int altro_snapshot(altro_handle_t h)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(h->X_snap, h->X, (size_t)h->B * h->N * h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->U_snap, h->U, (size_t)h->B * (h->N - 1) * h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->lam_snap, h->lam, (size_t)h->B * std::max(h->P, 1) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return ALTRO_OK;
+}
+
+int altro_restore(altro_handle_t h)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(h->X, h->X_snap, (size_t)h->B * h->N * h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->U, h->U_snap, (size_t)h->B * (h->N - 1) * h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->lam, h->lam_snap, (size_t)h->B * std::max(h->P, 1) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return ALTRO_OK;
+}
+
+int altro_set_track(altro_handle_t h, const double *tX, const double *tU, int Nt, const int *k_start)
+{
+    REQ(h);
+    if (!tX || !tU || Nt < 2 || !k_start) return fail(h, ALTRO_ERR_INVALID, "bad track");
+    if (h->trackX) { cudaFree(h->trackX); cudaFree(h->trackU); h->trackX = h->trackU = nullptr; }
+    CK(h, dalloc(&h->trackX, (size_t)Nt * h->n));
+    CK(h, dalloc(&h->trackU, (size_t)(Nt - 1) * h->m));
+    CK(h, cudaMemcpy(h->trackX, tX, (size_t)Nt * h->n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->trackU, tU, (size_t)(Nt - 1) * h->m * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->kidx, k_start, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice));
+    h->Nt = Nt;
+    return ALTRO_OK;
+}
+
+int altro_mpc_transition(altro_handle_t h, const double *noise, int shift)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (noise) {
+        rc = upload(h, h->noise, noise, (size_t)h->B * h->n);
+        if (rc) return rc;
+    }
+    mpc_transition_kernel<<<h->B, 64, 0, h->stream>>>(h->n, h->m, h->N, h->A, h->Bm, h->d, h->dyn_per_knot,
+                                                     h->dyn_per_instance, h->X, h->U, noise ? h->noise : nullptr,
+                                                     h->x0, h->trackX, h->trackU, h->Nt, h->kidx, h->xref, h->uref);
+    CK(h, cudaGetLastError());
+    h->have_x0 = true;
+    if (shift) return altro_shift_fill(h, 1, 1);
+    return ALTRO_OK;
+}
+
+int altro_host_register(void *ptr, size_t bytes)
+{
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) return fail(nullptr, ALTRO_ERR_CUDA, cudaGetErrorString(e));
+    return ALTRO_OK;
+}
+
+int altro_host_unregister(void *ptr)
+{
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) return fail(nullptr, ALTRO_ERR_CUDA, cudaGetErrorString(e));
+    return ALTRO_OK;
+}
+
+int altro_set_launch_config(altro_handle_t h, int threads)
+{
+    REQ(h);
+    if (h->finalized) return fail(h, ALTRO_ERR_STATE, "launch configuration is fixed after the first solve");
+    if (threads != 0 && threads != 32 && threads != 64 && threads != 128 && threads != 256)
+        return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 0 (auto), 32, 64, 128 or 256");
+    h->threads_req = threads;
+    return ALTRO_OK;
+}
+
+int altro_get_launch_info(altro_handle_t h, int *threads, int *smem, int *regs, int *ctas, int *sms)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (threads) *threads = h->threads;
+    if (smem) *smem = h->smem;
+    if (regs) *regs = h->regs;
+    if (ctas) *ctas = h->ctas_per_sm;
+    if (sms) *sms = h->num_sms;
+    return ALTRO_OK;
+}
+
+int altro_measure_peaks(int device, double *dfma, double *dmma, double *copy_gbs)
+{
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, ALTRO_ERR_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess)
+        return fail(nullptr, ALTRO_ERR_CUDA, "cudaMalloc");
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float ms = 0.f;
+    if (dfma) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(a);
+            dfma_peak_kernel<<<blocks, threads>>>(out, iters);
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            cudaEventElapsedTime(&ms, a, b);
+            double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+        *dfma = best;
+    }
+    if (dmma) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(a);
+            dmma_peak_kernel<<<blocks, threads>>>(out, iters / 4);
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            cudaEventElapsedTime(&ms, a, b);
+            double fl = 2.0 * 8 * 8 * 4 * 4.0 * (iters / 4) * (double)blocks * (threads / 32);
+            if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+        *dmma = best;
+    }
+    if (copy_gbs) {
+        const size_t bytes = (size_t)1 << 30;
+        char *s = nullptr, *d = nullptr;
+        if (cudaMalloc(&s, bytes) == cudaSuccess && cudaMalloc(&d, bytes) == cudaSuccess) {
+            double best = 0.0;
+            for (int rep = 0; rep < 4; ++rep) {
+                cudaEventRecord(a);
+                cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice);
+                cudaEventRecord(b);
+                cudaEventSynchronize(b);
+                cudaEventElapsedTime(&ms, a, b);
+                if (rep > 0) best = std::max(best, 2.0 * bytes / (ms * 1e-3) / 1e9);
+            }
+            *copy_gbs = best;
+        } else *copy_gbs = 0.0;
+        if (s) cudaFree(s);
+        if (d) cudaFree(d);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, ALTRO_ERR_CUDA, cudaGetErrorString(e));
+    return ALTRO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,889 @@
+// altro_kernels.cuh -- batched AL-iLQR (ALTRO) solve for sm_100a: one CTA per MPC instance.
+//
+// The whole solve! of one instance -- AL outer loop, iLQR inner loop, Riccati backward pass,
+// line-searched forward rollouts, AL cost / expansion, dual and penalty updates (SURVEY.md 8a rows
+// a1-a10; reference call sites random_linear_problem.jl:161, simple_rocket.jl:174, altro_solver.jl:72,
+// grasp_mpc.jl:55, flexible_sat_mpc.jl:272) -- runs inside ONE kernel launch with the instance's
+// trajectories, gains, duals and Riccati blocks resident in shared memory.  No host round trip per
+// iteration; instances never synchronise with each other, so divergent iteration counts cost nothing
+// but their own CTA's time and the hardware block scheduler balances the tail.
+//
+// Template <NX, NU, T>: state / control dimension (0 = run-time value from Params) and threads per
+// instance (32 = one warp, __syncwarp only; 64..256 = CTA with __syncthreads).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/altro_b200.h"
+
+namespace altro {
+
+constexpr int MAX_CON = 16;  // constraint blocks per problem
+constexpr int MAX_W = 32;    // index-set width of one block
+constexpr int PMAX = 16;     // rows of a dense block (row-sparse blocks are unlimited)
+constexpr int TRACE_COLS = 10;  // outer, iter, J, dJ, grad, rho, dV1, dV2, ls trials so far, c_max (NaN inside an outer)
+
+// One affine conic block c = G z[inds] + h (device view).
+struct ConDesc {
+    int sense, side, k0, k1, p, w;
+    int per_knot, per_instance;
+    int rowsparse;  // every row of G has <= 1 nonzero (bounds): value = h[r] + rs_coef[r] * z[inds[rs_col[r]]]
+    int dual_off;   // offset of the block in the per-instance dual vector
+    int ex_off;     // offset of the block in the per-instance expansion scratch
+    int ex_stride;  // per-knot stride there: w + w*w (dense) or 2*w (row-sparse)
+    const double *G, *h;
+    const int *rs_col;
+    const double *rs_coef;
+    int inds[MAX_W];
+};
+
+struct Params {
+    int n, m, N, B, P, ncon, EX;
+    int inst_offset;
+    double dt;
+    int dyn_per_knot, dyn_per_instance, dyn_in_smem, ref_in_smem;
+    const double *A, *Bm, *d;
+    const double *Q, *R, *Qf;
+    const double *xref, *uref, *x0;
+    double *X, *U, *lam;
+    int *iters, *outer, *status, *trials;
+    double *cost, *cost_al, *cmax, *penmax;
+    long long *t_ns;
+    double *trace;  // optional [B][trace_rows][TRACE_COLS] per-iteration log (verbose mode), or nullptr
+    int trace_rows;
+    const ConDesc *con;
+    altro_opts_t o;
+};
+
+// Shared-memory footprint in doubles (host and device must agree).
+__host__ __device__ inline size_t smem_doubles(int n, int m, int N, int P, int ncon, int EX, int dyn_in_smem,
+                                                int ref_in_smem, int T)
+{
+    size_t s = 0;
+    s += (size_t)2 * n + m;                                   // Q, Qf, R
+    s += dyn_in_smem ? (size_t)n * n + (size_t)n * m + n : 0;  // shared LTI dynamics
+    s += (size_t)2 * ((size_t)N * n + (size_t)(N - 1) * m);   // X,U,Xb,Ub
+    s += ref_in_smem ? (size_t)N * n + (size_t)(N - 1) * m : 0;  // xref, uref
+    s += (size_t)(N - 1) * m * n + (size_t)(N - 1) * m;       // K, d
+    s += (size_t)P + MAX_CON;                                 // duals, penalties
+    s += (size_t)EX;                                          // expansion scratch
+    s += (size_t)3 * n * n + (size_t)n * m + (size_t)2 * m * n + (size_t)2 * m * m;  // S,SA,Qxx,SB,Qux,T1,Quu,L
+    s += (size_t)3 * n + (size_t)4 * m;                       // s,Qx,(spare) ; Qu,t1,ldiag,(spare)
+    s += (size_t)T / 32 + 8;                                  // reduction scratch + broadcast slots
+    s += (size_t)N * (1 + ncon);                              // per-(knot, piece) cost items
+    return s;
+}
+
+__host__ __device__ inline size_t smem_bytes(int n, int m, int N, int P, int ncon, int EX, int dyn_in_smem,
+                                              int ref_in_smem, int T)
+{
+    size_t b = smem_doubles(n, m, N, P, ncon, EX, dyn_in_smem, ref_in_smem, T) * sizeof(double);
+    b += (size_t)(ncon > 0 ? ncon : 1) * sizeof(ConDesc);
+    return (b + 15) & ~(size_t)15;
+}
+
+#ifdef __CUDACC__
+
+template <int T>
+__device__ __forceinline__ void gsync()
+{
+    if (T == 32) __syncwarp();
+    else __syncthreads();
+}
+
+// Canonical sum of arr[0..count): lane l of warp 0 adds arr[l], arr[l+32], ... in order, then an
+// xor-butterfly over the 32 partials.  The summation order does not depend on T, so the CPU oracle
+// can reproduce every cost / gradient value bit for bit.  arr must be visible to warp 0 on entry.
+template <int T>
+__device__ __forceinline__ double csum(const double *arr, int count, double *bc)
+{
+    double v = 0.0;
+    if (T == 32 || threadIdx.x < 32) {
+        for (int i = threadIdx.x; i < count; i += 32) v += arr[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    if (T == 32) return v;
+    if (threadIdx.x == 0) bc[2] = v;
+    __syncthreads();
+    v = bc[2];
+    __syncthreads();
+    return v;
+}
+
+// Max over the instance's T threads (order independent, exact); every thread gets the same value.
+template <int T>
+__device__ __forceinline__ double gmax(double v, double *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (T == 32) return v;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = red[0];
+#pragma unroll
+    for (int i = 1; i < T / 32; ++i) s = fmax(s, red[i]);
+    return s;
+}
+
+// Per-instance context: shared-memory pointers and problem view.
+template <int NX, int NU, int T>
+struct Ctx {
+    const Params &P;
+    int n, m, N, inst, tid, ncon;
+    // shared memory
+    double *Qd, *Qfd, *Rd, *sA, *sB, *sd;
+    double *X, *U, *Xb, *Ub, *xr, *ur, *K, *dv, *lam, *mu, *ex;
+    double *S, *SA, *Qxx, *SB, *Qux, *T1, *Quu, *L, *s, *Qx, *Qu, *t1, *ldiag, *red, *bc, *itm;
+    ConDesc *cd;
+    size_t dyn_base;
+    int dyn_k;
+
+    __device__ Ctx(const Params &P_, unsigned char *raw) : P(P_)
+    {
+        n = NX ? NX : P.n;
+        m = NU ? NU : P.m;
+        N = P.N;
+        ncon = P.ncon;
+        tid = threadIdx.x;
+        inst = blockIdx.x + P.inst_offset;
+        double *q = reinterpret_cast<double *>(raw);
+        Qd = q; q += n;
+        Qfd = q; q += n;
+        Rd = q; q += m;
+        if (P.dyn_in_smem) { sA = q; q += n * n; sB = q; q += n * m; sd = q; q += n; }
+        else sA = sB = sd = nullptr;
+        X = q; q += N * n;
+        U = q; q += (N - 1) * m;
+        Xb = q; q += N * n;
+        Ub = q; q += (N - 1) * m;
+        if (P.ref_in_smem) { xr = q; q += N * n; ur = q; q += (N - 1) * m; }
+        else {  // large horizons: read the reference through L1/L2 instead
+            xr = const_cast<double *>(P.xref) + (size_t)inst * N * n;
+            ur = const_cast<double *>(P.uref) + (size_t)inst * (N - 1) * m;
+        }
+        K = q; q += (N - 1) * m * n;
+        dv = q; q += (N - 1) * m;
+        lam = q; q += P.P;
+        mu = q; q += MAX_CON;
+        ex = q; q += P.EX;
+        S = q; q += n * n;
+        SA = q; q += n * n;
+        Qxx = q; q += n * n;
+        SB = q; q += n * m;
+        Qux = q; q += m * n;
+        T1 = q; q += m * n;
+        Quu = q; q += m * m;
+        L = q; q += m * m;
+        s = q; q += n;
+        Qx = q; q += n;
+        q += n;
+        Qu = q; q += m;
+        t1 = q; q += m;
+        ldiag = q; q += m;
+        q += m;
+        red = q; q += T / 32;
+        bc = q; q += 8;
+        itm = q; q += N * (1 + ncon);
+        cd = reinterpret_cast<ConDesc *>(q);
+        dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_per_knot ? (size_t)(N - 1) : 1) : 0;
+        dyn_k = P.dyn_per_knot ? 1 : 0;
+    }
+
+    __device__ __forceinline__ const double *Ak(int k) const
+    {
+        return P.dyn_in_smem ? sA : P.A + (dyn_base + (size_t)dyn_k * k) * n * n;
+    }
+    __device__ __forceinline__ const double *Bk(int k) const
+    {
+        return P.dyn_in_smem ? sB : P.Bm + (dyn_base + (size_t)dyn_k * k) * n * m;
+    }
+    __device__ __forceinline__ const double *dk(int k) const
+    {
+        return P.dyn_in_smem ? sd : P.d + (dyn_base + (size_t)dyn_k * k) * n;
+    }
+    __device__ __forceinline__ size_t con_idx(const ConDesc &c, int k) const
+    {
+        size_t idx = c.per_instance ? (size_t)inst * (c.per_knot ? (size_t)(c.k1 - c.k0) : 1) : 0;
+        return idx + (c.per_knot ? (size_t)(k - c.k0) : 0);
+    }
+
+    // ---------------------------------------------------------------- load / store
+    __device__ void load()
+    {
+        for (int i = tid; i < n; i += T) { Qd[i] = P.Q[i]; Qfd[i] = P.Qf[i]; }
+        for (int i = tid; i < m; i += T) Rd[i] = P.R[i];
+        if (P.dyn_in_smem) {
+            for (int i = tid; i < n * n; i += T) sA[i] = P.A[i];
+            for (int i = tid; i < n * m; i += T) sB[i] = P.Bm[i];
+            for (int i = tid; i < n; i += T) sd[i] = P.d[i];
+        }
+        const double *gx0 = P.x0 + (size_t)inst * n;
+        for (int i = tid; i < n; i += T) X[i] = gx0[i];
+        const double *gU = P.U + (size_t)inst * (N - 1) * m;
+        for (int i = tid; i < (N - 1) * m; i += T) U[i] = gU[i];
+        const double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
+        if (P.ref_in_smem) {
+            for (int i = tid; i < N * n; i += T) xr[i] = gxr[i];
+            for (int i = tid; i < (N - 1) * m; i += T) ur[i] = gur[i];
+        }
+        const double *gl = P.lam + (size_t)inst * P.P;
+        const bool rd = P.o.reset_duals != 0;
+        for (int i = tid; i < P.P; i += T) lam[i] = rd ? 0.0 : gl[i];
+        for (int i = tid; i < MAX_CON; i += T) mu[i] = P.o.penalty_initial;
+        const int words = ncon * (int)(sizeof(ConDesc) / sizeof(int));
+        const int *src = reinterpret_cast<const int *>(P.con);
+        int *dst = reinterpret_cast<int *>(cd);
+        for (int i = tid; i < words; i += T) dst[i] = src[i];
+        gsync<T>();
+    }
+
+    __device__ void store()
+    {
+        double *gX = P.X + (size_t)inst * N * n, *gU = P.U + (size_t)inst * (N - 1) * m;
+        for (int i = tid; i < N * n; i += T) gX[i] = X[i];
+        for (int i = tid; i < (N - 1) * m; i += T) gU[i] = U[i];
+        double *gl = P.lam + (size_t)inst * P.P;
+        for (int i = tid; i < P.P; i += T) gl[i] = lam[i];
+    }
+
+    // ---------------------------------------------------------------- constraint values
+    // Row r of block c at knot k evaluated on z (x_k or u_k): TO.evaluate.
+    __device__ __forceinline__ double row_value(const ConDesc &c, const double *G, const double *h, const double *z,
+                                                int r) const
+    {
+        if (c.rowsparse) return fma(c.rs_coef[r], z[c.inds[c.rs_col[r]]], h[r]);
+        double acc = h[r];
+        const double *g = G + r * c.w;
+        for (int j = 0; j < c.w; ++j) acc = fma(g[j], z[c.inds[j]], acc);
+        return acc;
+    }
+
+    // AL penalty term of block ci at knot k (Altro cost!(J, conval)); SURVEY.md A.3.
+    __device__ double con_cost(int ci, int k, const double *Xc, const double *Uc) const
+    {
+        const ConDesc &c = cd[ci];
+        if (k < c.k0 || k >= c.k1) return 0.0;
+        const size_t di = con_idx(c, k);
+        const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
+        const double *z = c.side == ALTRO_STATE ? Xc + k * n : Uc + k * m;
+        const double *l = lam + c.dual_off + (k - c.k0) * c.p;
+        const double mu_c = mu[ci];
+        double J = 0.0;
+        if (c.sense == ALTRO_EQUALITY) {
+            for (int r = 0; r < c.p; ++r) {
+                double v = row_value(c, G, h, z, r);
+                J += l[r] * v + 0.5 * mu_c * v * v;
+            }
+        } else if (c.sense == ALTRO_INEQUALITY) {
+            for (int r = 0; r < c.p; ++r) {
+                double v = row_value(c, G, h, z, r);
+                bool act = (v >= 0.0) || (l[r] > 0.0);
+                J += l[r] * v + (act ? 0.5 * mu_c * v * v : 0.0);
+            }
+        } else {
+            double a2 = 0.0, t = 0.0, nl = 0.0;
+            for (int r = 0; r < c.p; ++r) {
+                double lb = l[r] - mu_c * row_value(c, G, h, z, r);
+                nl += l[r] * l[r];
+                if (r < c.p - 1) a2 += lb * lb;
+                else t = lb;
+            }
+            double a = sqrt(a2), np;
+            if (a <= -t) np = 0.0;
+            else if (a <= t) np = a2 + t * t;
+            else np = 0.5 * (a + t) * (a + t);
+            J = (np - nl) / (2.0 * mu_c);
+        }
+        return J;
+    }
+
+    __device__ double stage_cost(int k, const double *Xc, const double *Uc) const
+    {
+        const double *x = Xc + k * n, *r = xr + k * n;
+        double J = 0.0;
+        if (k == N - 1) {
+            for (int i = 0; i < n; ++i) { double e = x[i] - r[i]; J += 0.5 * Qfd[i] * e * e; }
+            return J;
+        }
+        for (int i = 0; i < n; ++i) { double e = x[i] - r[i]; J += 0.5 * Qd[i] * e * e; }
+        const double *u = Uc + k * m, *q = ur + k * m;
+        for (int i = 0; i < m; ++i) { double e = u[i] - q[i]; J += 0.5 * Rd[i] * e * e; }
+        return J * P.dt;
+    }
+
+    // AL cost of a trajectory: sum over (knot, piece) work items, one per thread.
+    __device__ double al_cost(const double *Xc, const double *Uc) const
+    {
+        const int items = N * (1 + ncon);
+        for (int it = tid; it < items; it += T) {
+            int k = it % N, j = it / N;
+            itm[it] = (j == 0) ? stage_cost(k, Xc, Uc) : con_cost(j - 1, k, Xc, Uc);
+        }
+        gsync<T>();
+        return csum<T>(itm, items, bc);
+    }
+
+    __device__ double objective_cost() const
+    {
+        for (int k = tid; k < N; k += T) itm[k] = stage_cost(k, X, U);
+        gsync<T>();
+        return csum<T>(itm, N, bc);
+    }
+
+    // max_violation
+    __device__ double max_violation() const
+    {
+        double v = 0.0;
+        for (int ci = 0; ci < ncon; ++ci) {
+            const ConDesc &c = cd[ci];
+            for (int k = c.k0 + tid; k < c.k1; k += T) {
+                const size_t di = con_idx(c, k);
+                const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
+                const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
+                if (c.sense == ALTRO_EQUALITY) {
+                    for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
+                } else if (c.sense == ALTRO_INEQUALITY) {
+                    for (int r = 0; r < c.p; ++r) v = fmax(v, row_value(c, G, h, z, r));
+                } else {
+                    double a2 = 0.0, t = 0.0;
+                    for (int r = 0; r < c.p; ++r) {
+                        double cv = row_value(c, G, h, z, r);
+                        if (r < c.p - 1) a2 += cv * cv;
+                        else t = cv;
+                    }
+                    double a = sqrt(a2);
+                    if (!P.o.soc_viol_proj) {
+                        v = fmax(v, a - t);
+                    } else if (a <= -t) {  // projection is 0: distance = |c|_inf
+                        for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
+                    } else if (a > t) {  // c - Pi(c) = ((1-cf) v, t - cf a)
+                        double cf = 0.5 * (1.0 + t / a);
+                        for (int r = 0; r < c.p - 1; ++r) v = fmax(v, fabs((1.0 - cf) * row_value(c, G, h, z, r)));
+                        v = fmax(v, fabs(t - cf * a));
+                    }
+                }
+            }
+        }
+        return gmax<T>(v, red);
+    }
+
+    // dual_update!: one (block, knot) per thread.
+    __device__ void dual_update()
+    {
+        for (int ci = 0; ci < ncon; ++ci) {
+            const ConDesc &c = cd[ci];
+            const double mu_c = mu[ci];
+            for (int k = c.k0 + tid; k < c.k1; k += T) {
+                const size_t di = con_idx(c, k);
+                const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
+                const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
+                double *l = lam + c.dual_off + (k - c.k0) * c.p;
+                if (c.sense == ALTRO_EQUALITY) {
+                    for (int r = 0; r < c.p; ++r)
+                        l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, r), -P.o.dual_max), P.o.dual_max);
+                } else if (c.sense == ALTRO_INEQUALITY) {
+                    for (int r = 0; r < c.p; ++r)
+                        l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, r), 0.0), P.o.dual_max);
+                } else {
+                    double a2 = 0.0, t = 0.0;
+                    for (int r = 0; r < c.p; ++r) {
+                        double lb = l[r] - mu_c * row_value(c, G, h, z, r);
+                        l[r] = lb;
+                        if (r < c.p - 1) a2 += lb * lb;
+                        else t = lb;
+                    }
+                    double a = sqrt(a2);
+                    if (a <= -t) {
+                        for (int r = 0; r < c.p; ++r) l[r] = 0.0;
+                    } else if (a > t) {
+                        double cf = 0.5 * (1.0 + t / a);
+                        for (int r = 0; r < c.p - 1; ++r) l[r] *= cf;
+                        l[c.p - 1] = cf * a;
+                    }
+                }
+            }
+        }
+        gsync<T>();
+    }
+
+    // ---------------------------------------------------------------- AL expansion
+    // Gradient g[w] and Hessian (w x w dense, or w diagonal for row-sparse blocks) of the AL term of
+    // every (block, knot) into the expansion scratch; one work item per thread.
+    __device__ void expand_constraints()
+    {
+        for (int ci = 0; ci < ncon; ++ci) {
+            const ConDesc &c = cd[ci];
+            const double mu_c = mu[ci];
+            const int w = c.w, p = c.p;
+            for (int k = c.k0 + tid; k < c.k1; k += T) {
+                const size_t di = con_idx(c, k);
+                const double *G = c.G + di * p * w, *h = c.h + di * p;
+                const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
+                const double *l = lam + c.dual_off + (k - c.k0) * p;
+                double *g = ex + c.ex_off + (k - c.k0) * c.ex_stride;
+                double *H = g + w;
+                if (c.rowsparse) {
+                    for (int j = 0; j < 2 * w; ++j) g[j] = 0.0;
+                    for (int r = 0; r < p; ++r) {
+                        double v = row_value(c, G, h, z, r), cf = c.rs_coef[r];
+                        bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l[r] > 0.0);
+                        int col = c.rs_col[r];
+                        g[col] += cf * (l[r] + (act ? mu_c * v : 0.0));
+                        H[col] += act ? cf * cf * mu_c : 0.0;
+                    }
+                } else if (c.sense != ALTRO_SECOND_ORDER_CONE) {
+                    double y[PMAX], D[PMAX];
+                    for (int r = 0; r < p; ++r) {
+                        double v = row_value(c, G, h, z, r);
+                        bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l[r] > 0.0);
+                        y[r] = l[r] + (act ? mu_c * v : 0.0);
+                        D[r] = act ? mu_c : 0.0;
+                    }
+                    for (int j = 0; j < w; ++j) {
+                        double acc = 0.0;
+                        for (int r = 0; r < p; ++r) acc = fma(G[r * w + j], y[r], acc);
+                        g[j] = acc;
+                    }
+                    for (int i = 0; i < w; ++i)
+                        for (int j = i; j < w; ++j) {
+                            double acc = 0.0;
+                            for (int r = 0; r < p; ++r) acc = fma(G[r * w + i] * D[r], G[r * w + j], acc);
+                            H[i * w + j] = acc;
+                            H[j * w + i] = acc;
+                        }
+                } else {
+                    // lb = lam - mu c ; Pi(lb) ; g = -G' Pi(lb) ; H = mu G' dPi(lb) G  (structured)
+                    double lb[PMAX], q[MAX_W];
+                    double a2 = 0.0;
+                    for (int r = 0; r < p; ++r) {
+                        lb[r] = l[r] - mu_c * row_value(c, G, h, z, r);
+                        if (r < p - 1) a2 += lb[r] * lb[r];
+                    }
+                    const double t = lb[p - 1], a = sqrt(a2);
+                    const double *gt = G + (p - 1) * w;
+                    if (a <= -t) {
+                        for (int j = 0; j < w + w * w; ++j) g[j] = 0.0;
+                    } else if (a <= t) {
+                        for (int j = 0; j < w; ++j) {
+                            double acc = 0.0;
+                            for (int r = 0; r < p; ++r) acc = fma(G[r * w + j], lb[r], acc);
+                            g[j] = -acc;
+                        }
+                        for (int i = 0; i < w; ++i)
+                            for (int j = i; j < w; ++j) {
+                                double acc = 0.0;
+                                for (int r = 0; r < p; ++r) acc = fma(G[r * w + i], G[r * w + j], acc);
+                                H[i * w + j] = mu_c * acc;
+                                H[j * w + i] = mu_c * acc;
+                            }
+                    } else {
+                        const double ia = 1.0 / a, cf = 0.5 * (1.0 + t * ia);
+                        const double cx = P.o.soc_hess_exact ? cf : cf * cf;
+                        // q = G' [xhat; 1],  xhat = v / a
+                        for (int j = 0; j < w; ++j) {
+                            double acc = 0.0;
+                            for (int r = 0; r < p - 1; ++r) acc = fma(G[r * w + j], lb[r], acc);
+                            q[j] = acc * ia;  // omega_hat
+                        }
+                        for (int i = 0; i < w; ++i)
+                            for (int j = i; j < w; ++j) {
+                                double gg = 0.0;
+                                for (int r = 0; r < p - 1; ++r) gg = fma(G[r * w + i], G[r * w + j], gg);
+                                double qi = q[i] + gt[i], qj = q[j] + gt[j];
+                                double hv = mu_c * (cx * (gg - q[i] * q[j]) + 0.5 * qi * qj);
+                                H[i * w + j] = hv;
+                                H[j * w + i] = hv;
+                            }
+                        for (int j = 0; j < w; ++j) g[j] = -cf * a * (q[j] + gt[j]);
+                    }
+                }
+            }
+        }
+        gsync<T>();
+    }
+
+    // Add the expansions of every block of `side` active at knot k into (vec, mat[ld x ld]).
+    __device__ void scatter_expansion(int k, int side, double *vec, double *mat, int ld)
+    {
+        for (int ci = 0; ci < ncon; ++ci) {
+            const ConDesc &c = cd[ci];
+            if (c.side != side || k < c.k0 || k >= c.k1) continue;  // uniform across the CTA
+            const double *g = ex + c.ex_off + (k - c.k0) * c.ex_stride;
+            const int w = c.w;
+            if (c.rowsparse) {
+                for (int e = tid; e < w; e += T) {
+                    int zi = c.inds[e];
+                    vec[zi] += g[e];
+                    mat[zi * ld + zi] += g[w + e];
+                }
+            } else {
+                for (int e = tid; e < w + w * w; e += T) {
+                    if (e < w) vec[c.inds[e]] += g[e];
+                    else {
+                        int i = (e - w) / w, j = (e - w) - i * w;
+                        mat[c.inds[i] * ld + c.inds[j]] += g[e];
+                    }
+                }
+            }
+            gsync<T>();
+        }
+    }
+
+    // ---------------------------------------------------------------- backward pass (A.7)
+    __device__ void reg_increase(double &rho, double &drho) const
+    {
+        drho = fmax(drho * P.o.bp_reg_increase_factor, P.o.bp_reg_increase_factor);
+        rho = fmax(rho * drho, P.o.bp_reg_min);
+    }
+    __device__ void reg_decrease(double &rho, double &drho) const
+    {
+        drho = fmin(drho / P.o.bp_reg_increase_factor, 1.0 / P.o.bp_reg_increase_factor);
+        double r = rho * drho;
+        rho = (r > P.o.bp_reg_min) ? r : 0.0;
+    }
+
+    // Returns false if Quu could not be made positive definite.
+    __device__ bool backward_pass(double &rho, double &drho, double &dV1, double &dV2)
+    {
+        expand_constraints();
+        for (;;) {
+            bool restart = false;
+            double a1 = 0.0, a2 = 0.0;  // dV accumulators, kept by thread T-1
+            // terminal cost-to-go: S = Qf + state-side AL Hessian, s = Qf (x - xref) + AL gradient
+            for (int e = tid; e < n * n; e += T) {
+                int i = e / n, j = e - i * n;
+                S[e] = (i == j) ? Qfd[i] : 0.0;
+            }
+            for (int i = tid; i < n; i += T) s[i] = Qfd[i] * (X[(N - 1) * n + i] - xr[(N - 1) * n + i]);
+            gsync<T>();
+            scatter_expansion(N - 1, ALTRO_STATE, s, S, n);
+            for (int k = N - 2; k >= 0; --k) {
+                const double *A = Ak(k), *Bm = Bk(k);
+                // P1: SA = S A, SB = S B ; cost expansion into Qxx,Quu,Qx,Qu
+                for (int e = tid; e < n * (n + m); e += T) {
+                    int i = e / (n + m), j = e - i * (n + m);
+                    const double *Si = S + i * n;
+                    double acc = 0.0;
+                    if (j < n) {
+                        for (int l = 0; l < n; ++l) acc = fma(Si[l], A[l * n + j], acc);
+                        SA[i * n + j] = acc;
+                    } else {
+                        j -= n;
+                        for (int l = 0; l < n; ++l) acc = fma(Si[l], Bm[l * m + j], acc);
+                        SB[i * m + j] = acc;
+                    }
+                }
+                for (int e = tid; e < n * n; e += T) {
+                    int i = e / n, j = e - i * n;
+                    Qxx[e] = (i == j) ? P.dt * Qd[i] : 0.0;
+                }
+                for (int e = tid; e < m * m; e += T) {
+                    int i = e / m, j = e - i * m;
+                    Quu[e] = (i == j) ? P.dt * Rd[i] : 0.0;
+                }
+                for (int i = tid; i < n; i += T) Qx[i] = P.dt * Qd[i] * (X[k * n + i] - xr[k * n + i]);
+                for (int i = tid; i < m; i += T) Qu[i] = P.dt * Rd[i] * (U[k * m + i] - ur[k * m + i]);
+                gsync<T>();
+                scatter_expansion(k, ALTRO_STATE, Qx, Qxx, n);
+                scatter_expansion(k, ALTRO_CONTROL, Qu, Quu, m);
+                // P2: Qxx += A'SA, Qux = B'SA, Quu += B'SB, Qx += A's, Qu += B's
+                const int o1 = n * n, o2 = o1 + m * n, o3 = o2 + m * m, o4 = o3 + n, o5 = o4 + m;
+                for (int e = tid; e < o5; e += T) {
+                    double acc = 0.0;
+                    if (e < o1) {
+                        int i = e / n, j = e - i * n;
+                        for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], SA[l * n + j], acc);
+                        Qxx[e] += acc;
+                    } else if (e < o2) {
+                        int f = e - o1, i = f / n, j = f - i * n;
+                        for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], SA[l * n + j], acc);
+                        Qux[f] = acc;
+                    } else if (e < o3) {
+                        int f = e - o2, i = f / m, j = f - i * m;
+                        for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], SB[l * m + j], acc);
+                        Quu[f] += acc;
+                    } else if (e < o4) {
+                        int i = e - o3;
+                        for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], s[l], acc);
+                        Qx[i] += acc;
+                    } else {
+                        int i = e - o4;
+                        for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], s[l], acc);
+                        Qu[i] += acc;
+                    }
+                }
+                gsync<T>();
+                // P3: Cholesky of Quu + rho I (left-looking, lower), diagonal kept in ldiag
+                for (int e = tid; e < m * m; e += T) {
+                    int i = e / m, j = e - i * m;
+                    L[e] = Quu[e] + ((i == j) ? rho : 0.0);
+                }
+                gsync<T>();
+                bool bad = false;
+                for (int j = 0; j < m; ++j) {
+                    for (int i = j + tid; i < m; i += T) {
+                        double acc = L[i * m + j];
+                        for (int l = 0; l < j; ++l) acc = fma(-L[i * m + l], L[j * m + l], acc);
+                        L[i * m + j] = acc;
+                    }
+                    gsync<T>();
+                    double dsum = L[j * m + j];
+                    if (!(dsum > 0.0)) { bad = true; break; }  // same value in every thread
+                    double dj = sqrt(dsum);
+                    for (int i = j + 1 + tid; i < m; i += T) L[i * m + j] = L[i * m + j] / dj;
+                    if (tid == 0) ldiag[j] = dj;
+                    gsync<T>();
+                }
+                if (bad) { restart = true; break; }
+                // P4: K = -(L L')^-1 Qux, d = -(L L')^-1 Qu ; one right-hand side per thread
+                double *Kk = K + k * m * n, *dk_ = dv + k * m;
+                for (int c = tid; c <= n; c += T) {
+                    double *b = (c < n) ? Kk + c : dk_;
+                    const double *src = (c < n) ? Qux + c : Qu;
+                    const int st = (c < n) ? n : 1;
+                    for (int i = 0; i < m; ++i) {
+                        double acc = -src[i * st];
+                        for (int l = 0; l < i; ++l) acc = fma(-L[i * m + l], b[l * st], acc);
+                        b[i * st] = acc / ldiag[i];
+                    }
+                    for (int i = m - 1; i >= 0; --i) {
+                        double acc = b[i * st];
+                        for (int l = i + 1; l < m; ++l) acc = fma(-L[l * m + i], b[l * st], acc);
+                        b[i * st] = acc / ldiag[i];
+                    }
+                }
+                gsync<T>();
+                // P5: T1 = Quu K + Qux, t1 = Quu d + Qu
+                for (int e = tid; e < m * n + m; e += T) {
+                    if (e < m * n) {
+                        int i = e / n, j = e - i * n;
+                        double acc = Qux[e];
+                        for (int l = 0; l < m; ++l) acc = fma(Quu[i * m + l], Kk[l * n + j], acc);
+                        T1[e] = acc;
+                    } else {
+                        int i = e - m * n;
+                        double acc = Qu[i];
+                        for (int l = 0; l < m; ++l) acc = fma(Quu[i * m + l], dk_[l], acc);
+                        t1[i] = acc;
+                    }
+                }
+                gsync<T>();
+                // P6: S' = Qxx + K'T1 + Qux'K (into SA), s = Qx + K't1 + Qux'd, dV += [d'Qu, 1/2 d'Quu d]
+                for (int e = tid; e < n * n + n; e += T) {
+                    if (e < n * n) {
+                        int i = e / n, j = e - i * n;
+                        double acc = Qxx[e];
+                        for (int l = 0; l < m; ++l) acc = fma(Kk[l * n + i], T1[l * n + j], acc);
+                        for (int l = 0; l < m; ++l) acc = fma(Qux[l * n + i], Kk[l * n + j], acc);
+                        SA[e] = acc;
+                    } else {
+                        int i = e - n * n;
+                        double acc = Qx[i];
+                        for (int l = 0; l < m; ++l) acc = fma(Kk[l * n + i], t1[l], acc);
+                        for (int l = 0; l < m; ++l) acc = fma(Qux[l * n + i], dk_[l], acc);
+                        s[i] = acc;
+                    }
+                }
+                if (tid == T - 1) {
+                    for (int i = 0; i < m; ++i) {
+                        a1 = fma(dk_[i], Qu[i], a1);
+                        a2 = fma(0.5 * dk_[i], t1[i] - Qu[i], a2);
+                    }
+                }
+                gsync<T>();
+                // P7: symmetrise
+                for (int e = tid; e < n * n; e += T) {
+                    int i = e / n, j = e - i * n;
+                    S[e] = 0.5 * (SA[e] + SA[j * n + i]);
+                }
+                gsync<T>();
+            }
+            if (restart) {
+                reg_increase(rho, drho);
+                if (rho > P.o.bp_reg_max) return false;
+                continue;
+            }
+            if (tid == T - 1) { bc[0] = a1; bc[1] = a2; }
+            gsync<T>();
+            dV1 = bc[0];
+            dV2 = bc[1];
+            gsync<T>();
+            reg_decrease(rho, drho);
+            return true;
+        }
+    }
+
+    // ---------------------------------------------------------------- rollouts (A.6, A.8)
+    __device__ void rollout_open_loop()
+    {
+        for (int k = 0; k < N - 1; ++k) {
+            const double *A = Ak(k), *Bm = Bk(k), *d = dk(k);
+            for (int i = tid; i < n; i += T) {
+                double acc = d[i];
+                for (int j = 0; j < n; ++j) acc = fma(A[i * n + j], X[k * n + j], acc);
+                for (int j = 0; j < m; ++j) acc = fma(Bm[i * m + j], U[k * m + j], acc);
+                X[(k + 1) * n + i] = acc;
+            }
+            gsync<T>();
+        }
+    }
+
+    // Closed-loop rollout with step alpha into Xb, Ub. Returns false if a state leaves the box.
+    __device__ bool rollout_alpha(double alpha)
+    {
+        for (int i = tid; i < n; i += T) Xb[i] = X[i];
+        gsync<T>();
+        double bad = 0.0;
+        for (int k = 0; k < N - 1; ++k) {
+            const double *A = Ak(k), *Bm = Bk(k), *d = dk(k);
+            const double *Kk = K + k * m * n;
+            for (int i = tid; i < m; i += T) {
+                double acc = fma(alpha, dv[k * m + i], U[k * m + i]);
+                for (int j = 0; j < n; ++j) acc = fma(Kk[i * n + j], Xb[k * n + j] - X[k * n + j], acc);
+                Ub[k * m + i] = acc;
+            }
+            gsync<T>();
+            for (int i = tid; i < n; i += T) {
+                double acc = d[i];
+                for (int j = 0; j < n; ++j) acc = fma(A[i * n + j], Xb[k * n + j], acc);
+                for (int j = 0; j < m; ++j) acc = fma(Bm[i * m + j], Ub[k * m + j], acc);
+                Xb[(k + 1) * n + i] = acc;
+                if (!(fabs(acc) <= P.o.max_state_value)) bad = 1.0;
+            }
+            gsync<T>();
+        }
+        return gmax<T>(bad, red) == 0.0;
+    }
+
+    __device__ void copy_traj(double *Xd, double *Ud, const double *Xs, const double *Us)
+    {
+        for (int i = tid; i < N * n; i += T) Xd[i] = Xs[i];
+        for (int i = tid; i < (N - 1) * m; i += T) Ud[i] = Us[i];
+        gsync<T>();
+    }
+
+    __device__ double forward_pass(double dV1, double dV2, double J_prev, double &rho, double &drho, int &trials)
+    {
+        double J = INFINITY, alpha = 1.0, z = -1.0;
+        int iter = 0;
+        while ((z <= P.o.line_search_lower_bound || z > P.o.line_search_upper_bound) && J >= J_prev) {
+            if (iter > P.o.iterations_linesearch) {
+                copy_traj(Xb, Ub, X, U);
+                J = al_cost(Xb, Ub);
+                reg_increase(rho, drho);
+                rho += P.o.bp_reg_fp;
+                break;
+            }
+            bool ok = rollout_alpha(alpha);
+            ++trials;
+            if (!ok) { ++iter; alpha *= 0.5; continue; }
+            J = al_cost(Xb, Ub);
+            double expected = -alpha * (dV1 + alpha * dV2);
+            z = expected > 0.0 ? (J_prev - J) / expected : -1.0;
+            ++iter;
+            alpha *= 0.5;
+        }
+        return J;
+    }
+
+    __device__ double gradient_todorov() const
+    {
+        for (int k = tid; k < N - 1; k += T) {
+            double mx = 0.0;
+            for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(dv[k * m + i]) / (fabs(U[k * m + i]) + 1.0));
+            itm[k] = mx;
+        }
+        gsync<T>();
+        return csum<T>(itm, N - 1, bc) / (double)(N - 1);
+    }
+
+    // ---------------------------------------------------------------- solve! (A.4 - A.6)
+    __device__ void solve()
+    {
+        long long t0 = 0;
+        if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        load();
+        const altro_opts_t &o = P.o;
+        int iters = 0, outer_done = 0, status = ALTRO_UNSOLVED, trials = 0;
+        double cmax = INFINITY, J = 0.0, pen_max = 0.0;
+        for (int outer = 1; outer <= o.iterations_outer; ++outer) {
+            outer_done = outer;
+            const bool last = (outer == o.iterations_outer) || ncon == 0;
+            const double ctol = last ? o.cost_tolerance : o.cost_tolerance_intermediate;
+            const double gtol = last ? o.gradient_tolerance : o.gradient_tolerance_intermediate;
+            double rho = o.bp_reg_initial, drho = 0.0;
+            int dJ_zero = 0;
+            rollout_open_loop();
+            double J_prev = al_cost(X, U);
+            J = J_prev;
+            for (int it = 0; it < o.iterations_inner; ++it) {
+                double dV1, dV2;
+                if (!backward_pass(rho, drho, dV1, dV2)) { status = ALTRO_NOT_PD; break; }
+                J = forward_pass(dV1, dV2, J_prev, rho, drho, trials);
+                if (J > o.max_cost_value || !(J == J)) { status = ALTRO_MAXIMUM_COST; break; }
+                copy_traj(X, U, Xb, Ub);
+                double dJ = fabs(J - J_prev);
+                J_prev = J;
+                double grad = gradient_todorov();
+                ++iters;
+                dJ_zero = (dJ == 0.0) ? dJ_zero + 1 : 0;
+                if (P.trace && tid == 0 && iters <= P.trace_rows) {
+                    double *tr = P.trace + ((size_t)inst * P.trace_rows + (iters - 1)) * TRACE_COLS;
+                    tr[0] = outer; tr[1] = iters; tr[2] = J; tr[3] = dJ; tr[4] = grad; tr[5] = rho;
+                    tr[6] = dV1; tr[7] = dV2; tr[8] = trials; tr[9] = nan("");
+                }
+                bool small = o.dj_zero_converges ? (dJ >= 0.0 && dJ < ctol) : (dJ > 0.0 && dJ < ctol);
+                if (small && grad < gtol) { status = ALTRO_SOLVE_SUCCEEDED; break; }
+                if (iters >= o.iterations) { status = ALTRO_MAX_ITERATIONS; break; }
+                if (dJ_zero > o.dJ_counter_limit) { status = ALTRO_NO_PROGRESS; break; }
+            }
+            if (status > ALTRO_SOLVE_SUCCEEDED) break;
+            cmax = max_violation();
+            if (P.trace && tid == 0 && iters >= 1 && iters <= P.trace_rows)
+                P.trace[((size_t)inst * P.trace_rows + (iters - 1)) * TRACE_COLS + 9] = cmax;
+            pen_max = 0.0;
+            for (int c = 0; c < ncon; ++c) pen_max = fmax(pen_max, mu[c]);
+            if (cmax < o.constraint_tolerance) break;
+            if (o.kickout_max_penalty && pen_max >= o.penalty_max) break;
+            dual_update();
+            if (tid < ncon) mu[tid] = fmin(mu[tid] * o.penalty_scaling, o.penalty_max);
+            gsync<T>();
+            if (outer == o.iterations_outer) status = ALTRO_MAX_ITERATIONS_OUTER;
+        }
+        cmax = max_violation();
+        if (status <= ALTRO_SOLVE_SUCCEEDED)
+            status = (cmax < o.constraint_tolerance) ? ALTRO_SOLVE_SUCCEEDED : ALTRO_UNSOLVED;
+        double Jobj = objective_cost();
+        store();
+        if (tid == 0) {
+            P.iters[inst] = iters;
+            P.outer[inst] = outer_done;
+            P.status[inst] = status;
+            P.trials[inst] = trials;
+            P.cost[inst] = Jobj;
+            P.cost_al[inst] = J;
+            P.cmax[inst] = cmax;
+            P.penmax[inst] = pen_max;
+            if (P.t_ns) {
+                long long t1v;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1v));
+                P.t_ns[inst] = t1v - t0;
+            }
+        }
+    }
+};
+
+template <int NX, int NU, int T>
+__global__ void __launch_bounds__(T) altro_solve_kernel(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx<NX, NU, T> ctx(P, smem_raw);
+    ctx.solve();
+}
+
+#endif  // __CUDACC__
+
+}  // namespace altro

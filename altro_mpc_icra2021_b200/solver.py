@@ -1,0 +1,329 @@
+"""ALTROSolver: the host-side mirror of Altro.ALTROSolver / solve! over the C ABI (include/altro_b200.h).
+
+Reference surface mirrored (paths relative to /root/reference/benchmarks):
+  ALTROSolver(prob, opts)          random_linear_mpc/random_linear_problem.jl:87, rocket_landing/simple_rocket.jl:128
+  solve!(altro)                    random_linear_problem.jl:113, simple_rocket.jl:174, quadruped/.../altro_solver.jl:72
+  benchmark_solve!(altro, ...)     random_linear_problem.jl:161
+  set_options!(solver; ...)        flexible_satellite/flexible_sat_mpc.jl:163,250-257
+  iterations / status / states / controls / cost / max_violation / stats.tsolve
+                                   random_linear_problem.jl:166-178, simple_rocket.jl:178-198, altro_solver.jl:75-79
+  Altro.shift_fill!(conSet) + RD.shift_fill!(Z)   random_linear_problem.jl:136,139, altro_solver.jl:65,68
+The Problem object is shared by reference with the solver and may be mutated between solves; solve()
+uploads whatever the mutators marked dirty, exactly like the Julia solver re-reads prob at every solve!.
+
+There is no CPU fallback: importing works anywhere, but constructing a solver without the compiled
+CUDA library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .problem import Problem, SolverOptions, STATUS_NAMES, SOLVE_SUCCEEDED
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaltro_b200.so")
+
+ABI_SYMBOLS = [
+    "altro_default_options", "altro_create", "altro_destroy", "altro_last_error", "altro_set_stream",
+    "altro_set_options", "altro_set_dynamics", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint",
+    "altro_update_constraint_data", "altro_set_x0", "altro_set_trajectory", "altro_get_trajectory", "altro_dual_len",
+    "altro_set_duals", "altro_get_duals", "altro_shift_fill", "altro_solve", "altro_sync", "altro_get_stats",
+    "altro_get_timing", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition",
+    "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
+    "altro_measure_peaks",
+]
+
+
+class AltroOpts(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "constraint_tolerance", "cost_tolerance", "cost_tolerance_intermediate", "gradient_tolerance",
+        "gradient_tolerance_intermediate", "penalty_initial", "penalty_scaling", "penalty_max", "dual_max",
+        "line_search_lower_bound", "line_search_upper_bound", "max_cost_value", "max_state_value",
+        "bp_reg_initial", "bp_reg_increase_factor", "bp_reg_max", "bp_reg_min", "bp_reg_fp")] + [
+        (k, C.c_int) for k in (
+            "iterations", "iterations_inner", "iterations_outer", "iterations_linesearch", "dJ_counter_limit",
+            "reset_duals", "reset_penalties", "kickout_max_penalty", "dj_zero_converges", "soc_hess_exact",
+            "soc_viol_proj")]
+
+
+class AltroError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libaltro_b200.so (built in-tree by __graft_entry__.build / csrc/Makefile). Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AltroError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                             f"g.build()'` (make -C altro_mpc_icra2021_b200/csrc). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.altro_last_error.restype = C.c_char_p
+        lib.altro_last_error.argtypes = [C.c_void_p]
+        for name in ABI_SYMBOLS:
+            fn = getattr(lib, name)
+            if name != "altro_last_error":
+                fn.restype = C.c_int
+        lib.altro_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+        _lib = lib
+    return _lib
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"] and a.dtype in (np.float64, np.int32, np.int64), (a.dtype, a.flags)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class SolverStats:
+    """solver.stats of the reference, per instance."""
+
+    iterations: np.ndarray
+    iterations_outer: np.ndarray
+    status: np.ndarray
+    ls_trials: np.ndarray
+    cost: np.ndarray
+    cost_al: np.ndarray
+    c_max: np.ndarray
+    penalty_max: np.ndarray
+    tsolve: float  # ms, device time of the batched solve
+    t_instance_us: np.ndarray  # per-instance solve time on the device, microseconds
+
+    @property
+    def status_names(self):
+        return [STATUS_NAMES[s] for s in self.status]
+
+
+class ALTROSolver:
+    def __init__(self, prob: Problem, opts: Optional[SolverOptions] = None, device: int = 0,
+                 threads_per_instance: int = 0, stream: Optional[int] = None, pin: bool = False, **kwargs):
+        self.lib = load_library()
+        self.prob = prob
+        self.opts = (opts or SolverOptions()).copy()
+        for k, v in kwargs.items():  # ALTROSolver(prob, opts; kwargs...) overrides (run_simple_rocket.jl:66)
+            setattr(self.opts, k, v)
+        self.h = C.c_void_p()
+        self._pinned = []
+        rc = self.lib.altro_create(C.byref(self.h), device, prob.n, prob.m, prob.N, prob.B, prob.dt)
+        if rc != 0:
+            raise AltroError(f"altro_create failed ({rc}): {self.lib.altro_last_error(None).decode()}")
+        if stream is not None:
+            self._ck(self.lib.altro_set_stream(self.h, C.c_void_p(stream)))
+        if threads_per_instance:
+            self._ck(self.lib.altro_set_launch_config(self.h, threads_per_instance))
+        self._ck(self.lib.altro_set_cost_diag(self.h, _p(prob.obj.Q), _p(prob.obj.R), _p(prob.obj.Qf)))
+        for c in prob.constraints.flat:
+            cid = C.c_int()
+            inds = np.ascontiguousarray(c.inds, dtype=np.int32)
+            self._ck(self.lib.altro_add_constraint(self.h, c.sense, c.side, c.k0, c.k1, c.p, c.w, _p(inds),
+                                                   int(c.per_knot), int(c.per_instance), _p(c.G), _p(c.h),
+                                                   C.byref(cid)))
+        prob.dirty["con"] = set()
+        self.P = prob.constraints.dual_len()
+        if pin:
+            for a in (prob.x0, prob.Xref, prob.Uref, prob.X, prob.U, prob.model.A, prob.model.B, prob.model.d):
+                if self.lib.altro_host_register(_p(a), C.c_size_t(a.nbytes)) == 0:
+                    self._pinned.append(a)
+        self._opts_dirty = True
+        self.stats: Optional[SolverStats] = None
+        self._results_stale = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc: int) -> None:
+        if rc != 0:
+            raise AltroError(f"altro error {rc}: {self.lib.altro_last_error(self.h).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "h", None) and self.h.value:
+            for a in self._pinned:
+                self.lib.altro_host_unregister(_p(a))
+            self.lib.altro_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_options(self, **kwargs) -> None:
+        """set_options!(solver; ...)."""
+        for k, v in kwargs.items():
+            if not hasattr(self.opts, k):
+                raise AttributeError(k)
+            setattr(self.opts, k, v)
+        self._opts_dirty = True
+
+    def _push_options(self) -> None:
+        o = AltroOpts()
+        for name, _ in AltroOpts._fields_:
+            setattr(o, name, getattr(self.opts, name))
+        self._ck(self.lib.altro_set_options(self.h, C.byref(o)))
+        self._opts_dirty = False
+
+    def upload(self) -> None:
+        """Pushes every dirty piece of the shared Problem to the device (async on the solver's stream)."""
+        p, d = self.prob, self.prob.dirty
+        if self._opts_dirty:
+            self._push_options()
+        if d["dyn"]:
+            mdl = p.model
+            self._ck(self.lib.altro_set_dynamics(self.h, int(mdl.per_knot), int(mdl.per_instance), _p(mdl.A),
+                                                 _p(mdl.B), _p(mdl.d)))
+            d["dyn"] = False
+        if d["ref"]:
+            self._ck(self.lib.altro_set_reference(self.h, _p(p.Xref), _p(p.Uref)))
+            d["ref"] = False
+        if d["x0"]:
+            self._ck(self.lib.altro_set_x0(self.h, _p(p.x0)))
+            d["x0"] = False
+        if d["traj"]:
+            self._ck(self.lib.altro_set_trajectory(self.h, _p(p.X), _p(p.U)))
+            d["traj"] = False
+        for cid in sorted(d["con"]):
+            c = p.constraints.flat[cid]
+            self._ck(self.lib.altro_update_constraint_data(self.h, cid, _p(c.G), _p(c.h)))
+        d["con"] = set()
+
+    # ------------------------------------------------------------------ solve!
+    def solve(self, fetch: bool = True) -> "ALTROSolver":
+        """solve!(solver): upload dirty problem data, run the batched AL-iLQR solve, and (fetch=True) bring
+        the trajectories and statistics back into prob.X / prob.U / self.stats."""
+        self.upload()
+        self._ck(self.lib.altro_solve(self.h))
+        self._results_stale = True
+        if fetch:
+            self.fetch()
+        return self
+
+    def fetch(self) -> SolverStats:
+        p, B = self.prob, self.prob.B
+        self._ck(self.lib.altro_get_trajectory(self.h, _p(p.X), _p(p.U)))
+        it, ito, st, ls = (np.zeros(B, np.int32) for _ in range(4))
+        cost, cal, cmax, pmax = (np.zeros(B) for _ in range(4))
+        self._ck(self.lib.altro_get_stats(self.h, _p(it), _p(ito), _p(st), _p(ls), _p(cost), _p(cal), _p(cmax),
+                                          _p(pmax)))
+        ms = C.c_double()
+        tns = np.zeros(B, np.int64)
+        self._ck(self.lib.altro_get_timing(self.h, C.byref(ms), _p(tns)))
+        self.stats = SolverStats(it, ito, st, ls, cost, cal, cmax, pmax, ms.value, tns / 1e3)
+        self._results_stale = False
+        return self.stats
+
+    def sync(self) -> None:
+        self._ck(self.lib.altro_sync(self.h))
+
+    def device_ms(self) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.altro_get_timing(self.h, C.byref(ms), None))
+        return ms.value
+
+    def benchmark_solve(self, samples: int = 10, evals: int = 10):
+        """benchmark_solve!(solver; samples, evals): snapshot the warm start, then repeat {restore; solve!}.
+        Duals are restored together with the primal trajectory.  Returns device times in ms."""
+        self.upload()
+        self._ck(self.lib.altro_snapshot(self.h))
+        times = []
+        for _ in range(samples * evals):
+            self._ck(self.lib.altro_restore(self.h))
+            self._ck(self.lib.altro_solve(self.h))
+            times.append(self.device_ms())
+        self.fetch()
+        return np.array(times)
+
+    # ------------------------------------------------------------------ warm-start shifts
+    def shift_fill(self, primal: bool = True, dual: bool = True) -> None:
+        """RD.shift_fill!(prob.Z) and Altro.shift_fill!(get_constraints(solver)), on the device."""
+        self.upload()
+        self._ck(self.lib.altro_shift_fill(self.h, int(primal), int(dual)))
+        if primal:  # keep the host mirror of the warm start consistent
+            p = self.prob
+            p.X[:, :-1] = p.X[:, 1:].copy()
+            if p.N > 2:
+                p.U[:, :-1] = p.U[:, 1:].copy()
+
+    def set_track(self, X_track, U_track, k_start) -> None:
+        Xt = np.ascontiguousarray(X_track, dtype=np.float64)
+        Ut = np.ascontiguousarray(U_track, dtype=np.float64)
+        ks = np.ascontiguousarray(k_start, dtype=np.int32)
+        self._ck(self.lib.altro_set_track(self.h, _p(Xt), _p(Ut), Xt.shape[0], _p(ks)))
+
+    def mpc_transition(self, noise: Optional[np.ndarray] = None, shift: bool = True) -> None:
+        """Device-side MPC step: plant step with the first control (+ noise), reference window advance
+        along the registered track, primal + dual shift.  No host traffic except the optional noise."""
+        self.upload()
+        nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
+        self._ck(self.lib.altro_mpc_transition(self.h, _p(nz), int(shift)))
+
+    # ------------------------------------------------------------------ queries
+    def states(self) -> np.ndarray:
+        return self.prob.X
+
+    def controls(self) -> np.ndarray:
+        return self.prob.U
+
+    def iterations(self) -> np.ndarray:
+        return self.stats.iterations
+
+    def status(self) -> np.ndarray:
+        return self.stats.status
+
+    def cost(self) -> np.ndarray:
+        return self.stats.cost
+
+    def max_violation(self) -> np.ndarray:
+        return self.stats.c_max
+
+    def get_duals(self) -> np.ndarray:
+        lam = np.zeros((self.prob.B, max(self.P, 1)))
+        if self.P:
+            self._ck(self.lib.altro_get_duals(self.h, _p(lam)))
+        return lam[:, :self.P]
+
+    def set_duals(self, lam: np.ndarray) -> None:
+        if self.P:
+            self._ck(self.lib.altro_set_duals(self.h, _p(np.ascontiguousarray(lam, dtype=np.float64))))
+
+    def set_trace(self, max_rows: int) -> None:
+        """verbose mode: keep a per-iteration log of every instance (see altro_set_trace)."""
+        self._ck(self.lib.altro_set_trace(self.h, int(max_rows)))
+        self._trace_rows = int(max_rows)
+
+    def get_trace(self) -> np.ndarray:
+        out = np.zeros((self.prob.B, self._trace_rows, 10))
+        self._ck(self.lib.altro_get_trace(self.h, _p(out)))
+        return out
+
+    def launch_info(self) -> dict:
+        self.upload()
+        v = [C.c_int() for _ in range(5)]
+        self._ck(self.lib.altro_get_launch_info(self.h, *[C.byref(x) for x in v]))
+        keys = ("threads_per_instance", "smem_bytes", "regs_per_thread", "ctas_per_sm", "num_sms")
+        return {k: x.value for k, x in zip(keys, v)}
+
+    def all_succeeded(self) -> bool:
+        return bool(np.all(self.stats.status == SOLVE_SUCCEEDED))
+
+
+def solve(solver: ALTROSolver) -> ALTROSolver:
+    """solve!(solver) spelled as a function, like the reference's call sites."""
+    return solver.solve()
+
+
+def measure_peaks(device: int = 0) -> dict:
+    lib = load_library()
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    rc = lib.altro_measure_peaks(device, C.byref(a), C.byref(b), C.byref(c))
+    if rc != 0:
+        raise AltroError(f"altro_measure_peaks failed: {lib.altro_last_error(None).decode()}")
+    return {"dfma_tflops": a.value, "dmma_tflops": b.value, "copy_gbs": c.value}

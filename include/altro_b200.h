@@ -1,0 +1,166 @@
+/*
+ * altro_b200.h -- C ABI of the B200-native batched ALTRO (augmented-Lagrangian iLQR) solver.
+ *
+ * The reference (RoboticExplorationLab/altro-mpc-icra2021) has no FFI on this path: its boundary
+ * is the Julia API of Altro.jl / TrajectoryOptimization.jl / RobotDynamics.jl as used by the
+ * benchmark scripts.  Every entry point below names the reference call it replaces (paths relative
+ * to /root/reference/benchmarks).  A Julia shim (julia/AltroB200.jl) binds these with `ccall` and
+ * re-exports the reference's names; altro_mpc_icra2021_b200/solver.py binds them with ctypes.
+ *
+ * Conventions
+ *   - one handle = one batch of B structurally identical problems on one GPU and one stream;
+ *     handles are independent and may be driven from different host threads; one handle is not
+ *     re-entrant.
+ *   - every pointer argument is a HOST pointer unless the name ends in _dev; buffers are caller
+ *     owned; layout is instance-major, row-major, FP64, 0-based knots k = 0..N-1 (controls 0..N-2).
+ *   - every function returns 0 on success or a negative altro_status_t error; altro_last_error()
+ *     gives the message.  There is no CPU fallback: a missing GPU is an error.
+ *   - setters enqueue an async H2D copy on the handle's stream (true DMA when the buffer was pinned
+ *     with altro_host_register); altro_solve enqueues the solve; getters synchronise the stream.
+ */
+#ifndef ALTRO_B200_H
+#define ALTRO_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct altro_handle_s *altro_handle_t;
+
+enum { ALTRO_OK = 0, ALTRO_ERR_INVALID = -1, ALTRO_ERR_CUDA = -2, ALTRO_ERR_UNSUPPORTED = -3, ALTRO_ERR_STATE = -4 };
+
+/* TrajectoryOptimization cone senses: Equality / Inequality / SecondOrderCone (scalar last). */
+enum { ALTRO_EQUALITY = 0, ALTRO_INEQUALITY = 1, ALTRO_SECOND_ORDER_CONE = 2 };
+enum { ALTRO_STATE = 0, ALTRO_CONTROL = 1 };
+
+/* Altro.TerminationStatus (random_linear_problem.jl:166, simple_rocket.jl:144,181). */
+enum {
+    ALTRO_UNSOLVED = 0, ALTRO_SOLVE_SUCCEEDED = 1, ALTRO_MAX_ITERATIONS = 2, ALTRO_MAX_ITERATIONS_OUTER = 3,
+    ALTRO_MAXIMUM_COST = 4, ALTRO_STATE_LIMIT = 5, ALTRO_CONTROL_LIMIT = 6, ALTRO_NO_PROGRESS = 7,
+    ALTRO_COST_INCREASE = 8, ALTRO_NOT_PD = 9
+};
+
+/* Altro.SolverOptions, field for field (run_random_linear.jl:41-49, run_simple_rocket.jl:121-129,
+ * ALTROParams.jl:86-95, grasp_benchmark.jl:26-34, flexible_sat_mpc.jl:250-257). */
+typedef struct altro_opts_t {
+    double constraint_tolerance;
+    double cost_tolerance, cost_tolerance_intermediate;
+    double gradient_tolerance, gradient_tolerance_intermediate;
+    double penalty_initial, penalty_scaling, penalty_max, dual_max;
+    double line_search_lower_bound, line_search_upper_bound;
+    double max_cost_value, max_state_value;
+    double bp_reg_initial, bp_reg_increase_factor, bp_reg_max, bp_reg_min, bp_reg_fp;
+    int iterations, iterations_inner, iterations_outer, iterations_linesearch;
+    int dJ_counter_limit;
+    int reset_duals, reset_penalties, kickout_max_penalty;
+    int dj_zero_converges; /* 1: 0<=dJ<tol converges, 0: 0<dJ<tol */
+    int soc_hess_exact;    /* 1: exact projection Hessian, 0: Gauss-Newton */
+    int soc_viol_proj;     /* 1: ||c-Pi(c)||_inf, 0: max(0,||v||-t) */
+} altro_opts_t;
+
+/* SolverOptions() defaults. */
+int altro_default_options(altro_opts_t *opts);
+
+/* ALTROSolver(prob, opts) (random_linear_problem.jl:87, simple_rocket.jl:128, ALTROParams.jl:96):
+ * size(prob) = (n,m,N), batch B, dt = stage-cost scaling (prob.Z[1].dt). */
+int altro_create(altro_handle_t *h, int device, int n, int m, int N, int batch, double dt);
+int altro_destroy(altro_handle_t h);
+const char *altro_last_error(altro_handle_t h); /* h may be NULL: last error of a failed create */
+
+/* Use a caller-provided cudaStream_t (e.g. torch's current stream) instead of the handle's own. */
+int altro_set_stream(altro_handle_t h, void *cuda_stream);
+
+/* SolverOptions(...) / set_options!(solver; ...) (flexible_sat_mpc.jl:163,250-257, grasp_mpc.jl:36). */
+int altro_set_options(altro_handle_t h, const altro_opts_t *opts);
+
+/* RD.LinearModel(A,B[,d]) and its in-place update opt.model.A[i] = ... (altro_solver.jl:35-37):
+ * x+ = A x + B u + d.  A[inst?][knot?][n][n], B[..][n][m], d[..][n] (d may be NULL = 0). */
+int altro_set_dynamics(altro_handle_t h, int per_knot, int per_instance, const double *A, const double *B,
+                       const double *d);
+
+/* LQRObjective / TrackingObjective diagonal weights (mpc.jl:26-29, ALTROParams.jl:46-47,81). */
+int altro_set_cost_diag(altro_handle_t h, const double *Q, const double *R, const double *Qf);
+
+/* TO.update_trajectory!(obj, Z_track, k) (random_linear_problem.jl:133, simple_rocket.jl:75):
+ * Xref[B][N][n], Uref[B][N-1][m]; the cost is centred on it (q = -Q xref, r = -R uref). */
+int altro_set_reference(altro_handle_t h, const double *Xref, const double *Uref);
+
+/* TO.add_constraint!(cons, con, inds) (random_linear_problem.jl:24, rocket_landing_problem.jl:96-167,
+ * ALTROParams.jl:65-78, grasp_problem.jl:35-67) for one affine conic block
+ *   c(z) = G z[inds] + h,  z = x_k or u_k,  knots [k0,k1),  p rows, w indices.
+ * G[inst?][knot?][p][w], h[..][p].  Must precede the first solve.  Returns the block id. */
+int altro_add_constraint(altro_handle_t h, int sense, int side, int k0, int k1, int p, int w, const int *inds,
+                         int per_knot, int per_instance, const double *G, const double *hvec, int *con_id);
+
+/* In-place constraint data update cons[1].A[i] = ... (grasp_mpc_helpers.jl:46-55). */
+int altro_update_constraint_data(altro_handle_t h, int con_id, const double *G, const double *hvec);
+
+/* TO.set_initial_state!(prob, x0) / problem.x0 .= x0 (random_linear_problem.jl:130, flexible_sat_mpc.jl:271). */
+int altro_set_x0(altro_handle_t h, const double *x0);
+
+/* initial_states!/initial_controls! and states()/controls() (altro_solver.jl:70-71,78-79).
+ * X[B][N][n], U[B][N-1][m]; either may be NULL. */
+int altro_set_trajectory(altro_handle_t h, const double *X, const double *U);
+int altro_get_trajectory(altro_handle_t h, double *X, double *U);
+
+/* Altro.get_duals (run_random_linear.jl:88): lam[B][P], P = sum over blocks of (k1-k0)*p. */
+int altro_dual_len(altro_handle_t h, int *P);
+int altro_set_duals(altro_handle_t h, const double *lam);
+int altro_get_duals(altro_handle_t h, double *lam);
+
+/* RD.shift_fill!(Z) and Altro.shift_fill!(conSet) (random_linear_problem.jl:136,139,
+ * simple_rocket.jl:78,81, altro_solver.jl:65,68): z_k <- z_{k+1}, last knot kept. On device. */
+int altro_shift_fill(altro_handle_t h, int primal, int dual);
+
+/* solve!(solver) (random_linear_problem.jl:113,161 ... ): enqueues the batched AL-iLQR solve. */
+int altro_solve(altro_handle_t h);
+int altro_sync(altro_handle_t h);
+
+/* iterations(s), status(s), s.stats, cost(s), max_violation(s) (random_linear_problem.jl:166-171,
+ * altro_solver.jl:75-76, simple_rocket.jl:178-198).  Arrays of length B; any may be NULL. */
+int altro_get_stats(altro_handle_t h, int *iterations, int *iterations_outer, int *status, int *ls_trials,
+                    double *cost, double *cost_al, double *c_max, double *penalty_max);
+
+/* s.stats.tsolve: device time of the last altro_solve in ms (CUDA events on the solve stream);
+ * per_instance_ns[B] (optional) = completion time of each instance since kernel start. */
+int altro_get_timing(altro_handle_t h, double *device_ms, long long *per_instance_ns);
+
+/* SolverOptions(verbose=...) (run_simple_rocket.jl:66,92): per-iteration log of every instance,
+ * max_rows iLQR iterations x 10 columns {outer, iteration, J, dJ, gradient, rho, dV1, dV2,
+ * line-search trials so far, c_max (NaN unless the iteration closed an outer loop)}; 0 disables. */
+int altro_set_trace(altro_handle_t h, int max_rows);
+int altro_get_trace(altro_handle_t h, double *out /* [B][max_rows][10] */);
+
+/* benchmark_solve!(solver) restore-and-resolve semantics (random_linear_problem.jl:161):
+ * snapshot / restore of (X, U, duals) on the device. */
+int altro_snapshot(altro_handle_t h);
+int altro_restore(altro_handle_t h);
+
+/* Device-side MPC transition between two solves (random_linear_problem.jl:121-139,
+ * simple_rocket.jl:59-82): x0 <- A_0 x_0 + B_0 u_0 + d_0 + noise_dev[inst][n] (noise may be NULL),
+ * then reference window advanced by one knot along a device-resident track
+ * (track_X_dev[Nt][n], track_U_dev[Nt-1][m], per-instance start index kept on the device),
+ * then primal + dual shift_fill.  Registers the track with altro_set_track. */
+int altro_set_track(altro_handle_t h, const double *track_X, const double *track_U, int Nt, const int *k_start);
+int altro_mpc_transition(altro_handle_t h, const double *noise /* host [B][n] or NULL */, int shift);
+
+/* Pin / unpin a caller buffer so setters and getters DMA directly (cudaHostRegister). */
+int altro_host_register(void *ptr, size_t bytes);
+int altro_host_unregister(void *ptr);
+
+/* Launch geometry of the solve kernel: threads per instance, dynamic shared memory bytes per
+ * instance (CTA), registers per thread, resident CTAs per SM. threads=0 in the setter = automatic. */
+int altro_set_launch_config(altro_handle_t h, int threads_per_instance);
+int altro_get_launch_info(altro_handle_t h, int *threads_per_instance, int *smem_bytes, int *regs_per_thread,
+                          int *ctas_per_sm, int *num_sms);
+
+/* FP64 roofline denominators measured on `device`: dependent-free DFMA stream and
+ * mma.sync m8n8k4 f64 stream (TFLOP/s), and a device copy (GB/s). Any may be NULL. */
+int altro_measure_peaks(int device, double *dfma_tflops, double *dmma_tflops, double *copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALTRO_B200_H */

@@ -15,6 +15,11 @@
 #include <pthread.h>
 #include <stdatomic.h>
 
+/* optional per-iteration log, same columns as the product's altro_set_trace */
+static double *orc_trace_buf = NULL;
+static int orc_trace_rows = 0;
+void orc_set_trace(double *buf, int rows) { orc_trace_buf = buf; orc_trace_rows = rows; }
+
 void orc_default_opts(orc_opts_t *o)
 {
     /* Altro.SolverOptions defaults */
@@ -100,34 +105,58 @@ void orc_soc_project_jac(int p, const double *v, double *J)
 
 /* ---------------------------------------------------------------- workspace */
 
+/* Arithmetic contract.  Every floating-point expression below is written in the same operation
+ * order as the CUDA kernel (altro_mpc_icra2021_b200/csrc/altro_kernels.cuh) with fused multiply-adds
+ * only where fma() is spelled out; this file is built with -ffp-contract=off and the kernel with
+ * -fmad=false, so both sides evaluate identical IEEE-754 sequences and the parity tests can demand
+ * bit-identical trajectories and iteration counts.  This matters because AL-iLQR on conic problems
+ * is a semismooth Newton method: at a point that lies on a cone boundary to the last bit (a warm
+ * start copied from an active reference) the Hessian branch is decided by one ulp. */
+
 typedef struct {
-    int n, m, N, P, pmax, wmax;
+    int n, m, N, P, EX, pmax, wmax, ncon;
     double *X, *U, *Xb, *Ub, *K, *dv;
-    double *S, *s, *SA, *SB, *Qxx, *Qux, *Quu, *L, *Qx, *Qu, *T1, *t1;
-    double *lxx, *luu;
-    double *mu;
-    double *cv, *y, *lp, *D, *DG, *g, *H;
-    int *off;
+    double *S, *s, *SA, *SB, *Qxx, *Qux, *Quu, *L, *Qx, *Qu, *T1, *t1, *ldiag;
+    double *mu, *ex, *itm;
+    int *off, *ex_off, *ex_stride, *rowsparse, *rs_col;
+    double *rs_coef;
+    int *rs_base;
 } ws_t;
 
 static double *dalloc(size_t k) { return (double *)calloc(k ? k : 1, sizeof(double)); }
+static int *ialloc(size_t k) { return (int *)calloc(k ? k : 1, sizeof(int)); }
 
 static ws_t *ws_new(const orc_problem_t *pb)
 {
     ws_t *w = (ws_t *)calloc(1, sizeof(ws_t));
-    int n = pb->n, m = pb->m, N = pb->N;
-    w->n = n; w->m = m; w->N = N;
-    w->P = orc_dual_len(pb);
-    w->pmax = 1; w->wmax = 1;
-    w->off = (int *)calloc((size_t)pb->ncon + 1, sizeof(int));
-    int P = 0;
-    for (int c = 0; c < pb->ncon; ++c) {
+    int n = pb->n, m = pb->m, N = pb->N, nc = pb->ncon;
+    w->n = n; w->m = m; w->N = N; w->ncon = nc;
+    w->off = ialloc(nc + 1); w->ex_off = ialloc(nc + 1); w->ex_stride = ialloc(nc + 1);
+    w->rowsparse = ialloc(nc + 1); w->rs_base = ialloc(nc + 1);
+    int P = 0, EX = 0, rows = 0;
+    for (int c = 0; c < nc; ++c) rows += pb->con[c].p;
+    w->rs_col = ialloc(rows); w->rs_coef = dalloc(rows);
+    rows = 0;
+    for (int c = 0; c < nc; ++c) {
+        const orc_con_t *cc = &pb->con[c];
         w->off[c] = P;
-        P += (pb->con[c].k1 - pb->con[c].k0) * pb->con[c].p;
-        if (pb->con[c].p > w->pmax) w->pmax = pb->con[c].p;
-        if (pb->con[c].w > w->wmax) w->wmax = pb->con[c].w;
+        w->ex_off[c] = EX;
+        w->rs_base[c] = rows;
+        /* row-sparse blocks (bounds): shared data, not a cone, every row has at most one nonzero */
+        int rs = !cc->per_knot && !cc->per_instance && cc->sense != ORC_SOC;
+        for (int r = 0; r < cc->p && rs; ++r) {
+            int nz = 0;
+            for (int j = 0; j < cc->w; ++j)
+                if (cc->G[r * cc->w + j] != 0.0) { ++nz; w->rs_col[rows + r] = j; w->rs_coef[rows + r] = cc->G[r * cc->w + j]; }
+            rs = nz <= 1;
+        }
+        w->rowsparse[c] = rs;
+        w->ex_stride[c] = rs ? 2 * cc->w : cc->w + cc->w * cc->w;
+        P += (cc->k1 - cc->k0) * cc->p;
+        EX += (cc->k1 - cc->k0) * w->ex_stride[c];
+        rows += cc->p;
     }
-    int pm = w->pmax, wm = w->wmax;
+    w->P = P; w->EX = EX;
     w->X = dalloc((size_t)N * n); w->Xb = dalloc((size_t)N * n);
     w->U = dalloc((size_t)(N - 1) * m); w->Ub = dalloc((size_t)(N - 1) * m);
     w->K = dalloc((size_t)(N - 1) * m * n); w->dv = dalloc((size_t)(N - 1) * m);
@@ -136,12 +165,8 @@ static ws_t *ws_new(const orc_problem_t *pb)
     w->Qxx = dalloc((size_t)n * n); w->Qux = dalloc((size_t)m * n);
     w->Quu = dalloc((size_t)m * m); w->L = dalloc((size_t)m * m);
     w->Qx = dalloc(n); w->Qu = dalloc(m);
-    w->T1 = dalloc((size_t)m * n); w->t1 = dalloc(m);
-    w->lxx = dalloc((size_t)n * n); w->luu = dalloc((size_t)m * m);
-    w->mu = dalloc(pb->ncon);
-    w->cv = dalloc(pm); w->y = dalloc(pm); w->lp = dalloc(pm);
-    w->D = dalloc((size_t)pm * pm); w->DG = dalloc((size_t)pm * wm);
-    w->g = dalloc(wm); w->H = dalloc((size_t)wm * wm);
+    w->T1 = dalloc((size_t)m * n); w->t1 = dalloc(m); w->ldiag = dalloc(m);
+    w->mu = dalloc(nc); w->ex = dalloc(EX); w->itm = dalloc((size_t)N * (1 + nc));
     return w;
 }
 
@@ -149,10 +174,26 @@ static void ws_free(ws_t *w)
 {
     free(w->X); free(w->Xb); free(w->U); free(w->Ub); free(w->K); free(w->dv);
     free(w->S); free(w->s); free(w->SA); free(w->SB); free(w->Qxx); free(w->Qux);
-    free(w->Quu); free(w->L); free(w->Qx); free(w->Qu); free(w->T1); free(w->t1);
-    free(w->lxx); free(w->luu); free(w->mu);
-    free(w->cv); free(w->y); free(w->lp); free(w->D); free(w->DG); free(w->g); free(w->H);
-    free(w->off); free(w);
+    free(w->Quu); free(w->L); free(w->Qx); free(w->Qu); free(w->T1); free(w->t1); free(w->ldiag);
+    free(w->mu); free(w->ex); free(w->itm);
+    free(w->off); free(w->ex_off); free(w->ex_stride); free(w->rowsparse); free(w->rs_base);
+    free(w->rs_col); free(w->rs_coef); free(w);
+}
+
+/* Canonical sum: 32 strided partials, then an xor-butterfly (the kernel's csum). */
+static double csum(const double *arr, int count)
+{
+    double v[32], t[32];
+    for (int l = 0; l < 32; ++l) {
+        double a = 0.0;
+        for (int i = l; i < count; i += 32) a += arr[i];
+        v[l] = a;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int l = 0; l < 32; ++l) t[l] = v[l] + v[l ^ o];
+        memcpy(v, t, sizeof v);
+    }
+    return v[0];
 }
 
 /* ---------------------------------------------------------------- data access */
@@ -177,14 +218,13 @@ static void con_ptrs(const orc_con_t *c, int inst, int k, const double **G, cons
     *h = c->h + idx * c->p;
 }
 
-/* c = G z[inds] + h  (TO.evaluate) */
-static void con_eval(const orc_con_t *c, const double *G, const double *h, const double *z, double *cv)
+/* Row r of c = G z[inds] + h  (TO.evaluate) */
+static double row_value(const orc_con_t *c, const double *G, const double *h, const double *z, int r)
 {
-    for (int r = 0; r < c->p; ++r) {
-        double acc = h[r];
-        for (int j = 0; j < c->w; ++j) acc += G[r * c->w + j] * z[c->inds[j]];
-        cv[r] = acc;
-    }
+    double acc = h[r];
+    const double *g = G + r * c->w;
+    for (int j = 0; j < c->w; ++j) acc = fma(g[j], z[c->inds[j]], acc);
+    return acc;
 }
 
 /* x+ = A x + B u + d  (discrete_dynamics of an affine RD.LinearModel) */
@@ -193,8 +233,8 @@ static void dyn_step(int n, int m, const double *A, const double *Bm, const doub
 {
     for (int i = 0; i < n; ++i) {
         double acc = d[i];
-        for (int j = 0; j < n; ++j) acc += A[i * n + j] * x[j];
-        for (int j = 0; j < m; ++j) acc += Bm[i * m + j] * u[j];
+        for (int j = 0; j < n; ++j) acc = fma(A[i * n + j], x[j], acc);
+        for (int j = 0; j < m; ++j) acc = fma(Bm[i * m + j], u[j], acc);
         xn[i] = acc;
     }
 }
@@ -212,29 +252,48 @@ static double stage_cost(const orc_problem_t *pb, int inst, int k, const double 
         for (int i = 0; i < n; ++i) { double e = x[i] - xr[i]; J += 0.5 * pb->Qf[i] * e * e; }
         return J;
     }
-    const double *ur = pb->uref + ((size_t)inst * (N - 1) + k) * m;
     for (int i = 0; i < n; ++i) { double e = x[i] - xr[i]; J += 0.5 * pb->Q[i] * e * e; }
+    const double *ur = pb->uref + ((size_t)inst * (N - 1) + k) * m;
     for (int i = 0; i < m; ++i) { double e = u[i] - ur[i]; J += 0.5 * pb->R[i] * e * e; }
     return J * pb->dt;
 }
 
-/* AL penalty term of one constraint block at one knot. */
-static double con_cost(const orc_con_t *c, const double *cv, const double *lam, double mu, double *lp)
+/* AL penalty term of block ci at knot k (Altro cost!(J, conval)). */
+static double con_cost(const orc_problem_t *pb, ws_t *w, int inst, int ci, int k, const double *X, const double *U,
+                       const double *lam)
 {
+    const orc_con_t *c = &pb->con[ci];
+    if (k < c->k0 || k >= c->k1) return 0.0;
+    const double *G, *h;
+    con_ptrs(c, inst, k, &G, &h);
+    const double *z = c->side == ORC_STATE ? X + (size_t)k * pb->n : U + (size_t)k * pb->m;
+    const double *l = lam + w->off[ci] + (k - c->k0) * c->p;
+    const double mu = w->mu[ci];
     double J = 0.0;
     if (c->sense == ORC_EQ) {
-        for (int r = 0; r < c->p; ++r) J += lam[r] * cv[r] + 0.5 * mu * cv[r] * cv[r];
+        for (int r = 0; r < c->p; ++r) {
+            double v = row_value(c, G, h, z, r);
+            J += l[r] * v + 0.5 * mu * v * v;
+        }
     } else if (c->sense == ORC_INEQ) {
         for (int r = 0; r < c->p; ++r) {
-            int act = (cv[r] >= 0.0) || (lam[r] > 0.0);
-            J += lam[r] * cv[r] + (act ? 0.5 * mu * cv[r] * cv[r] : 0.0);
+            double v = row_value(c, G, h, z, r);
+            int act = (v >= 0.0) || (l[r] > 0.0);
+            J += l[r] * v + (act ? 0.5 * mu * v * v : 0.0);
         }
     } else {
-        double nl = 0.0, np = 0.0;
-        double lb[ORC_MAX_W + 1];
-        for (int r = 0; r < c->p; ++r) { lb[r] = lam[r] - mu * cv[r]; nl += lam[r] * lam[r]; }
-        orc_soc_project(c->p, lb, lp);
-        for (int r = 0; r < c->p; ++r) np += lp[r] * lp[r];
+        /* 1/(2mu) (||Pi(lam - mu c)||^2 - ||lam||^2), with ||Pi(v,t)||^2 in closed form */
+        double a2 = 0.0, t = 0.0, nl = 0.0;
+        for (int r = 0; r < c->p; ++r) {
+            double lb = l[r] - mu * row_value(c, G, h, z, r);
+            nl += l[r] * l[r];
+            if (r < c->p - 1) a2 += lb * lb;
+            else t = lb;
+        }
+        double a = sqrt(a2), np;
+        if (a <= -t) np = 0.0;
+        else if (a <= t) np = a2 + t * t;
+        else np = 0.5 * (a + t) * (a + t);
         J = (np - nl) / (2.0 * mu);
     }
     return J;
@@ -243,55 +302,55 @@ static double con_cost(const orc_con_t *c, const double *cv, const double *lam, 
 static double al_cost(const orc_problem_t *pb, ws_t *w, int inst, const double *X, const double *U,
                       const double *lam)
 {
-    int n = pb->n, m = pb->m, N = pb->N;
-    double J = 0.0;
-    for (int k = 0; k < N; ++k) {
-        double Jk = stage_cost(pb, inst, k, X + (size_t)k * n, k < N - 1 ? U + (size_t)k * m : NULL);
-        for (int c = 0; c < pb->ncon; ++c) {
-            const orc_con_t *cc = &pb->con[c];
-            if (k < cc->k0 || k >= cc->k1) continue;
-            const double *G, *h;
-            con_ptrs(cc, inst, k, &G, &h);
-            const double *z = cc->side == ORC_STATE ? X + (size_t)k * n : U + (size_t)k * m;
-            con_eval(cc, G, h, z, w->cv);
-            Jk += con_cost(cc, w->cv, lam + w->off[c] + (k - cc->k0) * cc->p, w->mu[c], w->lp);
-        }
-        J += Jk;
+    int N = pb->N, items = N * (1 + pb->ncon);
+    for (int it = 0; it < items; ++it) {
+        int k = it % N, j = it / N;
+        w->itm[it] = (j == 0)
+            ? stage_cost(pb, inst, k, X + (size_t)k * pb->n, k < N - 1 ? U + (size_t)k * pb->m : NULL)
+            : con_cost(pb, w, inst, j - 1, k, X, U, lam);
     }
-    return J;
+    return csum(w->itm, items);
 }
 
-static double objective_cost(const orc_problem_t *pb, int inst, const double *X, const double *U)
+static double objective_cost(const orc_problem_t *pb, ws_t *w, int inst, const double *X, const double *U)
 {
-    double J = 0.0;
     for (int k = 0; k < pb->N; ++k)
-        J += stage_cost(pb, inst, k, X + (size_t)k * pb->n, k < pb->N - 1 ? U + (size_t)k * pb->m : NULL);
-    return J;
+        w->itm[k] = stage_cost(pb, inst, k, X + (size_t)k * pb->n, k < pb->N - 1 ? U + (size_t)k * pb->m : NULL);
+    return csum(w->itm, pb->N);
 }
 
 /* max_violation (A.3): eq |c|, ineq max(0,c), SOC distance to the cone. */
-static double max_violation(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, const double *X,
+static double max_violation(const orc_problem_t *pb, const orc_opts_t *o, int inst, const double *X,
                             const double *U)
 {
     double v = 0.0;
-    for (int c = 0; c < pb->ncon; ++c) {
-        const orc_con_t *cc = &pb->con[c];
-        for (int k = cc->k0; k < cc->k1; ++k) {
+    for (int ci = 0; ci < pb->ncon; ++ci) {
+        const orc_con_t *c = &pb->con[ci];
+        for (int k = c->k0; k < c->k1; ++k) {
             const double *G, *h;
-            con_ptrs(cc, inst, k, &G, &h);
-            const double *z = cc->side == ORC_STATE ? X + (size_t)k * pb->n : U + (size_t)k * pb->m;
-            con_eval(cc, G, h, z, w->cv);
-            if (cc->sense == ORC_EQ) {
-                for (int r = 0; r < cc->p; ++r) v = fmax(v, fabs(w->cv[r]));
-            } else if (cc->sense == ORC_INEQ) {
-                for (int r = 0; r < cc->p; ++r) v = fmax(v, w->cv[r]);
-            } else if (o->soc_viol_proj) {
-                orc_soc_project(cc->p, w->cv, w->lp);
-                for (int r = 0; r < cc->p; ++r) v = fmax(v, fabs(w->cv[r] - w->lp[r]));
+            con_ptrs(c, inst, k, &G, &h);
+            const double *z = c->side == ORC_STATE ? X + (size_t)k * pb->n : U + (size_t)k * pb->m;
+            if (c->sense == ORC_EQ) {
+                for (int r = 0; r < c->p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
+            } else if (c->sense == ORC_INEQ) {
+                for (int r = 0; r < c->p; ++r) v = fmax(v, row_value(c, G, h, z, r));
             } else {
-                double a = 0.0;
-                for (int r = 0; r < cc->p - 1; ++r) a += w->cv[r] * w->cv[r];
-                v = fmax(v, sqrt(a) - w->cv[cc->p - 1]);
+                double a2 = 0.0, t = 0.0;
+                for (int r = 0; r < c->p; ++r) {
+                    double cv = row_value(c, G, h, z, r);
+                    if (r < c->p - 1) a2 += cv * cv;
+                    else t = cv;
+                }
+                double a = sqrt(a2);
+                if (!o->soc_viol_proj) {
+                    v = fmax(v, a - t);
+                } else if (a <= -t) { /* projection is 0: distance = |c|_inf */
+                    for (int r = 0; r < c->p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
+                } else if (a > t) { /* c - Pi(c) = ((1-cf) v, t - cf a) */
+                    double cf = 0.5 * (1.0 + t / a);
+                    for (int r = 0; r < c->p - 1; ++r) v = fmax(v, fabs((1.0 - cf) * row_value(c, G, h, z, r)));
+                    v = fmax(v, fabs(t - cf * a));
+                }
             }
         }
     }
@@ -300,136 +359,126 @@ static double max_violation(const orc_problem_t *pb, const orc_opts_t *o, ws_t *
 
 /* ---------------------------------------------------------------- expansion (A.3) */
 
-/* Gradient g[w] and Hessian H[w][w] of one constraint block's AL term w.r.t. z[inds]. */
-static void con_expand(const orc_opts_t *o, ws_t *w, const orc_con_t *c, const double *G, const double *cv,
-                       const double *lam, double mu)
+/* Gradient g[w] and Hessian (w x w, or w diagonal entries for row-sparse blocks) of the AL term of
+ * every (block, knot) into the expansion scratch.  SOC blocks use the closed form of mu G' dPi G:
+ *   inside  (a <= t):  mu G'G,                                   g = -G' lb
+ *   outside (a >  t):  mu (cx (Gv'Gv - q q') + 1/2 (q+gt)(q+gt)'), g = -cf a (q + gt)
+ * with lb = lam - mu c = (v, t), a = |v|, q = Gv' v / a, gt = last row of G, cf = (1 + t/a)/2 and
+ * cx = cf (exact Hessian) or cf^2 (Gauss-Newton); orc_soc_project_jac is the dense cross-check. */
+static void expand_constraints(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, const double *lam)
 {
-    int p = c->p, wd = c->w;
-    double *D = w->D, *DG = w->DG, *y = w->y;
-    memset(D, 0, sizeof(double) * (size_t)p * p);
-    if (c->sense == ORC_EQ) {
-        for (int r = 0; r < p; ++r) { y[r] = lam[r] + mu * cv[r]; D[r * p + r] = mu; }
-    } else if (c->sense == ORC_INEQ) {
-        for (int r = 0; r < p; ++r) {
-            int act = (cv[r] >= 0.0) || (lam[r] > 0.0);
-            y[r] = lam[r] + (act ? mu * cv[r] : 0.0);
-            D[r * p + r] = act ? mu : 0.0;
-        }
-    } else {
-        double lb[ORC_MAX_W + 1];
-        for (int r = 0; r < p; ++r) lb[r] = lam[r] - mu * cv[r];
-        orc_soc_project(p, lb, w->lp);
-        for (int r = 0; r < p; ++r) y[r] = -w->lp[r];
-        orc_soc_project_jac(p, lb, D);
-        if (!o->soc_hess_exact) { /* Gauss-Newton: dPi' dPi */
-            double *T = (double *)malloc(sizeof(double) * (size_t)p * p);
-            for (int i = 0; i < p; ++i)
-                for (int j = 0; j < p; ++j) {
-                    double acc = 0.0;
-                    for (int l = 0; l < p; ++l) acc += D[l * p + i] * D[l * p + j];
-                    T[i * p + j] = acc;
+    for (int ci = 0; ci < pb->ncon; ++ci) {
+        const orc_con_t *c = &pb->con[ci];
+        const double mu = w->mu[ci];
+        const int wd = c->w, p = c->p;
+        for (int k = c->k0; k < c->k1; ++k) {
+            const double *G, *h;
+            con_ptrs(c, inst, k, &G, &h);
+            const double *z = c->side == ORC_STATE ? w->X + (size_t)k * pb->n : w->U + (size_t)k * pb->m;
+            const double *l = lam + w->off[ci] + (k - c->k0) * p;
+            double *g = w->ex + w->ex_off[ci] + (k - c->k0) * w->ex_stride[ci];
+            double *H = g + wd;
+            if (w->rowsparse[ci]) {
+                const int *col = w->rs_col + w->rs_base[ci];
+                const double *coef = w->rs_coef + w->rs_base[ci];
+                for (int j = 0; j < 2 * wd; ++j) g[j] = 0.0;
+                for (int r = 0; r < p; ++r) {
+                    double v = row_value(c, G, h, z, r), cf = coef[r];
+                    int act = c->sense == ORC_EQ || (v >= 0.0) || (l[r] > 0.0);
+                    g[col[r]] += cf * (l[r] + (act ? mu * v : 0.0));
+                    H[col[r]] += act ? cf * cf * mu : 0.0;
                 }
-            memcpy(D, T, sizeof(double) * (size_t)p * p);
-            free(T);
+            } else if (c->sense != ORC_SOC) {
+                double y[ORC_MAX_W], D[ORC_MAX_W];
+                for (int r = 0; r < p; ++r) {
+                    double v = row_value(c, G, h, z, r);
+                    int act = c->sense == ORC_EQ || (v >= 0.0) || (l[r] > 0.0);
+                    y[r] = l[r] + (act ? mu * v : 0.0);
+                    D[r] = act ? mu : 0.0;
+                }
+                for (int j = 0; j < wd; ++j) {
+                    double acc = 0.0;
+                    for (int r = 0; r < p; ++r) acc = fma(G[r * wd + j], y[r], acc);
+                    g[j] = acc;
+                }
+                for (int i = 0; i < wd; ++i)
+                    for (int j = i; j < wd; ++j) {
+                        double acc = 0.0;
+                        for (int r = 0; r < p; ++r) acc = fma(G[r * wd + i] * D[r], G[r * wd + j], acc);
+                        H[i * wd + j] = acc;
+                        H[j * wd + i] = acc;
+                    }
+            } else {
+                double lb[ORC_MAX_W], q[ORC_MAX_W];
+                double a2 = 0.0;
+                for (int r = 0; r < p; ++r) {
+                    lb[r] = l[r] - mu * row_value(c, G, h, z, r);
+                    if (r < p - 1) a2 += lb[r] * lb[r];
+                }
+                const double t = lb[p - 1], a = sqrt(a2);
+                const double *gt = G + (p - 1) * wd;
+                if (a <= -t) {
+                    for (int j = 0; j < wd + wd * wd; ++j) g[j] = 0.0;
+                } else if (a <= t) {
+                    for (int j = 0; j < wd; ++j) {
+                        double acc = 0.0;
+                        for (int r = 0; r < p; ++r) acc = fma(G[r * wd + j], lb[r], acc);
+                        g[j] = -acc;
+                    }
+                    for (int i = 0; i < wd; ++i)
+                        for (int j = i; j < wd; ++j) {
+                            double acc = 0.0;
+                            for (int r = 0; r < p; ++r) acc = fma(G[r * wd + i], G[r * wd + j], acc);
+                            H[i * wd + j] = mu * acc;
+                            H[j * wd + i] = mu * acc;
+                        }
+                } else {
+                    const double ia = 1.0 / a, cf = 0.5 * (1.0 + t * ia);
+                    const double cx = o->soc_hess_exact ? cf : cf * cf;
+                    for (int j = 0; j < wd; ++j) {
+                        double acc = 0.0;
+                        for (int r = 0; r < p - 1; ++r) acc = fma(G[r * wd + j], lb[r], acc);
+                        q[j] = acc * ia;
+                    }
+                    for (int i = 0; i < wd; ++i)
+                        for (int j = i; j < wd; ++j) {
+                            double gg = 0.0;
+                            for (int r = 0; r < p - 1; ++r) gg = fma(G[r * wd + i], G[r * wd + j], gg);
+                            double qi = q[i] + gt[i], qj = q[j] + gt[j];
+                            double hv = mu * (cx * (gg - q[i] * q[j]) + 0.5 * qi * qj);
+                            H[i * wd + j] = hv;
+                            H[j * wd + i] = hv;
+                        }
+                    for (int j = 0; j < wd; ++j) g[j] = -cf * a * (q[j] + gt[j]);
+                }
+            }
         }
-        for (int i = 0; i < p * p; ++i) D[i] *= mu;
     }
-    /* g = G' y ; H = G' D G */
-    for (int j = 0; j < wd; ++j) {
-        double acc = 0.0;
-        for (int r = 0; r < p; ++r) acc += G[r * wd + j] * y[r];
-        w->g[j] = acc;
-    }
-    for (int r = 0; r < p; ++r)
-        for (int j = 0; j < wd; ++j) {
-            double acc = 0.0;
-            for (int l = 0; l < p; ++l) acc += D[r * p + l] * G[l * wd + j];
-            DG[r * wd + j] = acc;
-        }
-    for (int i = 0; i < wd; ++i)
-        for (int j = 0; j < wd; ++j) {
-            double acc = 0.0;
-            for (int r = 0; r < p; ++r) acc += G[r * wd + i] * DG[r * wd + j];
-            w->H[i * wd + j] = acc;
-        }
 }
 
-/* Cost + AL expansion at knot k: lx[n], lxx[n][n], lu[m], luu[m][m] (cost_expansion!). */
-static void knot_expansion(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, int k,
-                           const double *lam, double *lx, double *lu)
+/* Add the expansions of every block of `side` active at knot k into (vec, mat[ld x ld]). */
+static void scatter_expansion(const orc_problem_t *pb, ws_t *w, int k, int side, double *vec, double *mat, int ld)
 {
-    int n = pb->n, m = pb->m, N = pb->N;
-    const double *x = w->X + (size_t)k * n;
-    const double *xr = pb->xref + ((size_t)inst * N + k) * n;
-    int term = (k == N - 1);
-    double sc = term ? 1.0 : pb->dt;
-    memset(w->lxx, 0, sizeof(double) * (size_t)n * n);
-    for (int i = 0; i < n; ++i) {
-        double q = term ? pb->Qf[i] : pb->Q[i];
-        lx[i] = sc * q * (x[i] - xr[i]);
-        w->lxx[i * n + i] = sc * q;
-    }
-    if (!term) {
-        const double *u = w->U + (size_t)k * m;
-        const double *ur = pb->uref + ((size_t)inst * (N - 1) + k) * m;
-        memset(w->luu, 0, sizeof(double) * (size_t)m * m);
-        for (int i = 0; i < m; ++i) {
-            lu[i] = sc * pb->R[i] * (u[i] - ur[i]);
-            w->luu[i * m + i] = sc * pb->R[i];
-        }
-    }
-    for (int c = 0; c < pb->ncon; ++c) {
-        const orc_con_t *cc = &pb->con[c];
-        if (k < cc->k0 || k >= cc->k1) continue;
-        const double *G, *h;
-        con_ptrs(cc, inst, k, &G, &h);
-        const double *z = cc->side == ORC_STATE ? x : w->U + (size_t)k * m;
-        con_eval(cc, G, h, z, w->cv);
-        con_expand(o, w, cc, G, w->cv, lam + w->off[c] + (k - cc->k0) * cc->p, w->mu[c]);
-        double *gv = cc->side == ORC_STATE ? lx : lu;
-        double *Hm = cc->side == ORC_STATE ? w->lxx : w->luu;
-        int ld = cc->side == ORC_STATE ? n : m;
-        for (int i = 0; i < cc->w; ++i) {
-            gv[cc->inds[i]] += w->g[i];
-            for (int j = 0; j < cc->w; ++j) Hm[cc->inds[i] * ld + cc->inds[j]] += w->H[i * cc->w + j];
+    for (int ci = 0; ci < pb->ncon; ++ci) {
+        const orc_con_t *c = &pb->con[ci];
+        if (c->side != side || k < c->k0 || k >= c->k1) continue;
+        const double *g = w->ex + w->ex_off[ci] + (k - c->k0) * w->ex_stride[ci];
+        const int wd = c->w;
+        if (w->rowsparse[ci]) {
+            for (int e = 0; e < wd; ++e) {
+                int zi = c->inds[e];
+                vec[zi] += g[e];
+                mat[zi * ld + zi] += g[wd + e];
+            }
+        } else {
+            for (int e = 0; e < wd; ++e) vec[c->inds[e]] += g[e];
+            for (int i = 0; i < wd; ++i)
+                for (int j = 0; j < wd; ++j) mat[c->inds[i] * ld + c->inds[j]] += g[wd + i * wd + j];
         }
     }
 }
 
 /* ---------------------------------------------------------------- backward pass (A.7) */
-
-/* In-place lower Cholesky of the m x m matrix L; returns 0 on success. */
-static int cholesky(int m, double *L)
-{
-    for (int j = 0; j < m; ++j) {
-        double dsum = L[j * m + j];
-        for (int l = 0; l < j; ++l) dsum -= L[j * m + l] * L[j * m + l];
-        if (!(dsum > 0.0)) return 1;
-        double dj = sqrt(dsum);
-        L[j * m + j] = dj;
-        for (int i = j + 1; i < m; ++i) {
-            double acc = L[i * m + j];
-            for (int l = 0; l < j; ++l) acc -= L[i * m + l] * L[j * m + l];
-            L[i * m + j] = acc / dj;
-        }
-    }
-    return 0;
-}
-
-/* Solve (L L') x = b in place. */
-static void chol_solve(int m, const double *L, double *b, int stride)
-{
-    for (int i = 0; i < m; ++i) {
-        double acc = b[i * stride];
-        for (int l = 0; l < i; ++l) acc -= L[i * m + l] * b[l * stride];
-        b[i * stride] = acc / L[i * m + i];
-    }
-    for (int i = m - 1; i >= 0; --i) {
-        double acc = b[i * stride];
-        for (int l = i + 1; l < m; ++l) acc -= L[l * m + i] * b[l * stride];
-        b[i * stride] = acc / L[i * m + i];
-    }
-}
 
 static void reg_increase(const orc_opts_t *o, double *rho, double *drho)
 {
@@ -448,105 +497,146 @@ static void reg_decrease(const orc_opts_t *o, double *rho, double *drho)
 static int backward_pass(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, const double *lam,
                          double *rho, double *drho, double dV[2])
 {
-    int n = pb->n, m = pb->m, N = pb->N;
-restart:
-    dV[0] = dV[1] = 0.0;
-    /* terminal cost-to-go */
-    knot_expansion(pb, o, w, inst, N - 1, lam, w->s, NULL);
-    memcpy(w->S, w->lxx, sizeof(double) * (size_t)n * n);
+    const int n = pb->n, m = pb->m, N = pb->N;
+    const double dt = pb->dt;
+    expand_constraints(pb, o, w, inst, lam);
+restart:;
+    double a1 = 0.0, a2 = 0.0;
+    /* terminal cost-to-go: S = Qf + state-side AL Hessian, s = Qf (x - xref) + AL gradient */
+    const double *xrN = pb->xref + ((size_t)inst * N + (N - 1)) * n;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) w->S[i * n + j] = (i == j) ? pb->Qf[i] : 0.0;
+    for (int i = 0; i < n; ++i) w->s[i] = pb->Qf[i] * (w->X[(size_t)(N - 1) * n + i] - xrN[i]);
+    scatter_expansion(pb, w, N - 1, ORC_STATE, w->s, w->S, n);
     for (int k = N - 2; k >= 0; --k) {
         const double *A, *Bm, *dd;
         dyn_ptrs(pb, inst, k, &A, &Bm, &dd);
-        knot_expansion(pb, o, w, inst, k, lam, w->Qx, w->Qu);
-        /* action-value expansion (_calc_Q!) */
+        const double *xr = pb->xref + ((size_t)inst * N + k) * n;
+        const double *ur = pb->uref + ((size_t)inst * (N - 1) + k) * m;
+        /* SA = S A, SB = S B */
         for (int i = 0; i < n; ++i) {
-            double acc = w->Qx[i];
-            for (int l = 0; l < n; ++l) acc += A[l * n + i] * w->s[l];
-            w->Qx[i] = acc;
-        }
-        for (int i = 0; i < m; ++i) {
-            double acc = w->Qu[i];
-            for (int l = 0; l < n; ++l) acc += Bm[l * m + i] * w->s[l];
-            w->Qu[i] = acc;
-        }
-        for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) {
                 double acc = 0.0;
-                for (int l = 0; l < n; ++l) acc += w->S[i * n + l] * A[l * n + j];
+                for (int l = 0; l < n; ++l) acc = fma(w->S[i * n + l], A[l * n + j], acc);
                 w->SA[i * n + j] = acc;
             }
-        for (int i = 0; i < n; ++i)
             for (int j = 0; j < m; ++j) {
                 double acc = 0.0;
-                for (int l = 0; l < n; ++l) acc += w->S[i * n + l] * Bm[l * m + j];
+                for (int l = 0; l < n; ++l) acc = fma(w->S[i * n + l], Bm[l * m + j], acc);
                 w->SB[i * m + j] = acc;
             }
+        }
+        /* cost expansion (diagonal LQR cost) + AL expansion */
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) w->Qxx[i * n + j] = (i == j) ? dt * pb->Q[i] : 0.0;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) w->Quu[i * m + j] = (i == j) ? dt * pb->R[i] : 0.0;
+        for (int i = 0; i < n; ++i) w->Qx[i] = dt * pb->Q[i] * (w->X[(size_t)k * n + i] - xr[i]);
+        for (int i = 0; i < m; ++i) w->Qu[i] = dt * pb->R[i] * (w->U[(size_t)k * m + i] - ur[i]);
+        scatter_expansion(pb, w, k, ORC_STATE, w->Qx, w->Qxx, n);
+        scatter_expansion(pb, w, k, ORC_CONTROL, w->Qu, w->Quu, m);
+        /* action-value expansion (_calc_Q!): Qxx += A'SA, Qux = B'SA, Quu += B'SB, Qx += A's, Qu += B's */
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) {
-                double acc = w->lxx[i * n + j];
-                for (int l = 0; l < n; ++l) acc += A[l * n + i] * w->SA[l * n + j];
-                w->Qxx[i * n + j] = acc;
-            }
-        for (int i = 0; i < m; ++i)
-            for (int j = 0; j < m; ++j) {
-                double acc = w->luu[i * m + j];
-                for (int l = 0; l < n; ++l) acc += Bm[l * m + i] * w->SB[l * m + j];
-                w->Quu[i * m + j] = acc;
+                double acc = 0.0;
+                for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], w->SA[l * n + j], acc);
+                w->Qxx[i * n + j] += acc;
             }
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < n; ++j) {
                 double acc = 0.0;
-                for (int l = 0; l < n; ++l) acc += Bm[l * m + i] * w->SA[l * n + j];
+                for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], w->SA[l * n + j], acc);
                 w->Qux[i * n + j] = acc;
             }
-        /* control regularisation (_bp_reg!, bp_reg_type = :control) and gains (_calc_gains!) */
-        memcpy(w->L, w->Quu, sizeof(double) * (size_t)m * m);
-        for (int i = 0; i < m; ++i) w->L[i * m + i] += *rho;
-        if (cholesky(m, w->L)) {
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) {
+                double acc = 0.0;
+                for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], w->SB[l * m + j], acc);
+                w->Quu[i * m + j] += acc;
+            }
+        for (int i = 0; i < n; ++i) {
+            double acc = 0.0;
+            for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], w->s[l], acc);
+            w->Qx[i] += acc;
+        }
+        for (int i = 0; i < m; ++i) {
+            double acc = 0.0;
+            for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], w->s[l], acc);
+            w->Qu[i] += acc;
+        }
+        /* control regularisation (_bp_reg!, :control) and left-looking Cholesky of Quu + rho I */
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) w->L[i * m + j] = w->Quu[i * m + j] + ((i == j) ? *rho : 0.0);
+        int bad = 0;
+        for (int j = 0; j < m && !bad; ++j) {
+            for (int i = j; i < m; ++i) {
+                double acc = w->L[i * m + j];
+                for (int l = 0; l < j; ++l) acc = fma(-w->L[i * m + l], w->L[j * m + l], acc);
+                w->L[i * m + j] = acc;
+            }
+            double dsum = w->L[j * m + j];
+            if (!(dsum > 0.0)) { bad = 1; break; }
+            double dj = sqrt(dsum);
+            for (int i = j + 1; i < m; ++i) w->L[i * m + j] = w->L[i * m + j] / dj;
+            w->ldiag[j] = dj;
+        }
+        if (bad) {
             reg_increase(o, rho, drho);
             if (*rho > o->bp_reg_max) return 1;
             goto restart;
         }
+        /* gains (_calc_gains!): K = -(L L')^-1 Qux, d = -(L L')^-1 Qu */
         double *K = w->K + (size_t)k * m * n, *dv = w->dv + (size_t)k * m;
-        for (int i = 0; i < m * n; ++i) K[i] = -w->Qux[i];
-        for (int i = 0; i < m; ++i) dv[i] = -w->Qu[i];
-        for (int j = 0; j < n; ++j) chol_solve(m, w->L, K + j, n);
-        chol_solve(m, w->L, dv, 1);
+        for (int c = 0; c <= n; ++c) {
+            double *b = (c < n) ? K + c : dv;
+            const double *src = (c < n) ? w->Qux + c : w->Qu;
+            const int st = (c < n) ? n : 1;
+            for (int i = 0; i < m; ++i) {
+                double acc = -src[i * st];
+                for (int l = 0; l < i; ++l) acc = fma(-w->L[i * m + l], b[l * st], acc);
+                b[i * st] = acc / w->ldiag[i];
+            }
+            for (int i = m - 1; i >= 0; --i) {
+                double acc = b[i * st];
+                for (int l = i + 1; l < m; ++l) acc = fma(-w->L[l * m + i], b[l * st], acc);
+                b[i * st] = acc / w->ldiag[i];
+            }
+        }
         /* cost-to-go (_calc_ctg!), unregularised Quu:  T1 = Quu K + Qux,  t1 = Quu d + Qu */
         for (int i = 0; i < m; ++i) {
             for (int j = 0; j < n; ++j) {
                 double acc = w->Qux[i * n + j];
-                for (int l = 0; l < m; ++l) acc += w->Quu[i * m + l] * K[l * n + j];
+                for (int l = 0; l < m; ++l) acc = fma(w->Quu[i * m + l], K[l * n + j], acc);
                 w->T1[i * n + j] = acc;
             }
             double acc = w->Qu[i];
-            for (int l = 0; l < m; ++l) acc += w->Quu[i * m + l] * dv[l];
+            for (int l = 0; l < m; ++l) acc = fma(w->Quu[i * m + l], dv[l], acc);
             w->t1[i] = acc;
         }
-        /* s = Qx + K'(Quu d + Qu) + Qux' d ;  S = Qxx + K'(Quu K + Qux) + Qux' K, symmetrised */
-        for (int i = 0; i < n; ++i) {
-            double acc = w->Qx[i];
-            for (int l = 0; l < m; ++l) acc += K[l * n + i] * w->t1[l];
-            for (int l = 0; l < m; ++l) acc += w->Qux[l * n + i] * dv[l];
-            w->s[i] = acc;
-        }
+        /* S' = Qxx + K'T1 + Qux'K, s = Qx + K't1 + Qux'd */
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) {
                 double acc = w->Qxx[i * n + j];
-                for (int l = 0; l < m; ++l) acc += K[l * n + i] * w->T1[l * n + j];
-                for (int l = 0; l < m; ++l) acc += w->Qux[l * n + i] * K[l * n + j];
+                for (int l = 0; l < m; ++l) acc = fma(K[l * n + i], w->T1[l * n + j], acc);
+                for (int l = 0; l < m; ++l) acc = fma(w->Qux[l * n + i], K[l * n + j], acc);
                 w->SA[i * n + j] = acc;
             }
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) w->S[i * n + j] = 0.5 * (w->SA[i * n + j] + w->SA[j * n + i]);
+        for (int i = 0; i < n; ++i) {
+            double acc = w->Qx[i];
+            for (int l = 0; l < m; ++l) acc = fma(K[l * n + i], w->t1[l], acc);
+            for (int l = 0; l < m; ++l) acc = fma(w->Qux[l * n + i], dv[l], acc);
+            w->s[i] = acc;
+        }
         /* expected change: [d'Qu, 1/2 d'Quu d] */
         for (int i = 0; i < m; ++i) {
-            dV[0] += dv[i] * w->Qu[i];
-            double acc = 0.0;
-            for (int l = 0; l < m; ++l) acc += w->Quu[i * m + l] * dv[l];
-            dV[1] += 0.5 * dv[i] * acc;
+            a1 = fma(dv[i], w->Qu[i], a1);
+            a2 = fma(0.5 * dv[i], w->t1[i] - w->Qu[i], a2);
         }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) w->S[i * n + j] = 0.5 * (w->SA[i * n + j] + w->SA[j * n + i]);
     }
+    dV[0] = a1;
+    dV[1] = a2;
     reg_decrease(o, rho, drho);
     return 0;
 }
@@ -556,7 +646,7 @@ restart:
 /* Closed-loop rollout with step alpha into Xb,Ub; returns 0 if a state leaves the box. */
 static int rollout_alpha(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, double alpha)
 {
-    int n = pb->n, m = pb->m, N = pb->N;
+    int n = pb->n, m = pb->m, N = pb->N, ok = 1;
     memcpy(w->Xb, w->X, sizeof(double) * n); /* x0 */
     for (int k = 0; k < N - 1; ++k) {
         const double *A, *Bm, *dd;
@@ -565,16 +655,15 @@ static int rollout_alpha(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, 
         double *xb = w->Xb + (size_t)k * n, *ub = w->Ub + (size_t)k * m;
         const double *x = w->X + (size_t)k * n, *u = w->U + (size_t)k * m;
         for (int i = 0; i < m; ++i) {
-            double acc = u[i] + alpha * dv[i];
-            for (int j = 0; j < n; ++j) acc += K[i * n + j] * (xb[j] - x[j]);
+            double acc = fma(alpha, dv[i], u[i]);
+            for (int j = 0; j < n; ++j) acc = fma(K[i * n + j], xb[j] - x[j], acc);
             ub[i] = acc;
         }
         dyn_step(n, m, A, Bm, dd, xb, ub, xb + n);
-        double mx = 0.0;
-        for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(xb[n + i]));
-        if (!(mx <= o->max_state_value)) return 0;
+        for (int i = 0; i < n; ++i)
+            if (!(fabs(xb[n + i]) <= o->max_state_value)) ok = 0;
     }
-    return 1;
+    return ok;
 }
 
 /* Returns the accepted cost J; *trials counts rollouts tried. */
@@ -610,24 +699,36 @@ static double forward_pass(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
 
 static void dual_update(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, double *lam)
 {
-    for (int c = 0; c < pb->ncon; ++c) {
-        const orc_con_t *cc = &pb->con[c];
-        double mu = w->mu[c];
-        for (int k = cc->k0; k < cc->k1; ++k) {
+    for (int ci = 0; ci < pb->ncon; ++ci) {
+        const orc_con_t *c = &pb->con[ci];
+        const double mu = w->mu[ci];
+        for (int k = c->k0; k < c->k1; ++k) {
             const double *G, *h;
-            con_ptrs(cc, inst, k, &G, &h);
-            const double *z = cc->side == ORC_STATE ? w->X + (size_t)k * pb->n : w->U + (size_t)k * pb->m;
-            con_eval(cc, G, h, z, w->cv);
-            double *l = lam + w->off[c] + (k - cc->k0) * cc->p;
-            if (cc->sense == ORC_EQ) {
-                for (int r = 0; r < cc->p; ++r)
-                    l[r] = fmin(fmax(l[r] + mu * w->cv[r], -o->dual_max), o->dual_max);
-            } else if (cc->sense == ORC_INEQ) {
-                for (int r = 0; r < cc->p; ++r) l[r] = fmin(fmax(l[r] + mu * w->cv[r], 0.0), o->dual_max);
-            } else {
-                double lb[ORC_MAX_W + 1];
-                for (int r = 0; r < cc->p; ++r) lb[r] = l[r] - mu * w->cv[r];
-                orc_soc_project(cc->p, lb, l);
+            con_ptrs(c, inst, k, &G, &h);
+            const double *z = c->side == ORC_STATE ? w->X + (size_t)k * pb->n : w->U + (size_t)k * pb->m;
+            double *l = lam + w->off[ci] + (k - c->k0) * c->p;
+            if (c->sense == ORC_EQ) {
+                for (int r = 0; r < c->p; ++r)
+                    l[r] = fmin(fmax(l[r] + mu * row_value(c, G, h, z, r), -o->dual_max), o->dual_max);
+            } else if (c->sense == ORC_INEQ) {
+                for (int r = 0; r < c->p; ++r)
+                    l[r] = fmin(fmax(l[r] + mu * row_value(c, G, h, z, r), 0.0), o->dual_max);
+            } else { /* lam <- Pi(lam - mu c) */
+                double a2 = 0.0, t = 0.0;
+                for (int r = 0; r < c->p; ++r) {
+                    double lb = l[r] - mu * row_value(c, G, h, z, r);
+                    l[r] = lb;
+                    if (r < c->p - 1) a2 += lb * lb;
+                    else t = lb;
+                }
+                double a = sqrt(a2);
+                if (a <= -t) {
+                    for (int r = 0; r < c->p; ++r) l[r] = 0.0;
+                } else if (a > t) {
+                    double cf = 0.5 * (1.0 + t / a);
+                    for (int r = 0; r < c->p - 1; ++r) l[r] *= cf;
+                    l[c->p - 1] = cf * a;
+                }
             }
         }
     }
@@ -647,6 +748,7 @@ static void solve_instance(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
     r->iters = r->outer = r->trials = 0;
     r->status = ORC_UNSOLVED;
     r->cmax = INFINITY;
+    r->pen_max = 0.0;
     if (o->reset_duals) memset(lam, 0, sizeof(double) * (size_t)w->P);
     for (int c = 0; c < pb->ncon; ++c) w->mu[c] = o->penalty_initial;
     double J = 0.0;
@@ -675,20 +777,20 @@ static void solve_instance(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
             memcpy(w->U, w->Ub, sizeof(double) * (size_t)(N - 1) * m);
             double dJ = fabs(J - J_prev);
             J_prev = J;
-            double grad = 0.0; /* gradient_todorov! */
-            for (int k = 0; k < N - 1; ++k) {
+            for (int k = 0; k < N - 1; ++k) { /* gradient_todorov! */
                 double mx = 0.0;
                 for (int i = 0; i < m; ++i)
                     mx = fmax(mx, fabs(w->dv[(size_t)k * m + i]) / (fabs(w->U[(size_t)k * m + i]) + 1.0));
-                grad += mx;
+                w->itm[k] = mx;
             }
-            grad /= (double)(N - 1);
+            double grad = csum(w->itm, N - 1) / (double)(N - 1);
             r->iters++;
             dJ_zero = (dJ == 0.0) ? dJ_zero + 1 : 0;
-#ifdef ORC_TRACE
-            fprintf(stderr, "inst %d outer %d it %d J %.17g dJ %.3e grad %.3e rho %.3e dV %.3e %.3e trials %d\n", inst,
-                    outer, r->iters, J, dJ, grad, rho, dV[0], dV[1], r->trials);
-#endif
+            if (orc_trace_buf && r->iters <= orc_trace_rows) {
+                double *tr = orc_trace_buf + ((size_t)inst * orc_trace_rows + (r->iters - 1)) * 10;
+                tr[0] = outer; tr[1] = r->iters; tr[2] = J; tr[3] = dJ; tr[4] = grad; tr[5] = rho;
+                tr[6] = dV[0]; tr[7] = dV[1]; tr[8] = r->trials; tr[9] = NAN;
+            }
             int small = o->dj_zero_converges ? (dJ >= 0.0 && dJ < ctol) : (dJ > 0.0 && dJ < ctol);
             if (small && grad < gtol) { r->status = ORC_SOLVE_SUCCEEDED; break; }
             if (r->iters >= o->iterations) { r->status = ORC_MAX_ITERATIONS; break; }
@@ -696,10 +798,9 @@ static void solve_instance(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
         }
         if (r->status > ORC_SOLVE_SUCCEEDED) break;
         /* ---- AL outer loop bookkeeping */
-        r->cmax = max_violation(pb, o, w, inst, w->X, w->U);
-#ifdef ORC_TRACE
-        fprintf(stderr, "inst %d outer %d cmax %.3e mu %.3e status %d\n", inst, outer, r->cmax, w->mu[0], r->status);
-#endif
+        r->cmax = max_violation(pb, o, inst, w->X, w->U);
+        if (orc_trace_buf && r->iters >= 1 && r->iters <= orc_trace_rows)
+            orc_trace_buf[((size_t)inst * orc_trace_rows + (r->iters - 1)) * 10 + 9] = r->cmax;
         r->pen_max = 0.0;
         for (int c = 0; c < pb->ncon; ++c) r->pen_max = fmax(r->pen_max, w->mu[c]);
         if (r->cmax < o->constraint_tolerance) break;
@@ -708,6 +809,7 @@ static void solve_instance(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
         for (int c = 0; c < pb->ncon; ++c) w->mu[c] = fmin(w->mu[c] * o->penalty_scaling, o->penalty_max);
         if (outer == o->iterations_outer) r->status = ORC_MAX_ITERATIONS_OUTER;
     }
+    r->cmax = max_violation(pb, o, inst, w->X, w->U);
     if (r->status <= ORC_SOLVE_SUCCEEDED)
         r->status = (r->cmax < o->constraint_tolerance) ? ORC_SOLVE_SUCCEEDED : ORC_UNSOLVED;
     r->J = J;
@@ -743,9 +845,9 @@ static void *worker(void *arg)
         if (j->iters_outer) j->iters_outer[i] = r.outer;
         if (j->status) j->status[i] = r.status;
         if (j->ls_trials) j->ls_trials[i] = r.trials;
-        if (j->cost) j->cost[i] = objective_cost(pb, i, w->X, w->U);
+        if (j->cost) j->cost[i] = objective_cost(pb, w, i, w->X, w->U);
         if (j->cost_al) j->cost_al[i] = r.J;
-        if (j->cmax) j->cmax[i] = max_violation(pb, j->o, w, i, w->X, w->U);
+        if (j->cmax) j->cmax[i] = r.cmax;
         if (j->pen_max) j->pen_max[i] = r.pen_max;
     }
     ws_free(w);
@@ -796,8 +898,8 @@ void orc_evaluate(const orc_problem_t *pb, const orc_opts_t *o, const double *X,
     ws_t *w = ws_new(pb);
     for (int i = 0; i < pb->B; ++i) {
         const double *x = X + (size_t)i * pb->N * pb->n, *u = U + (size_t)i * (pb->N - 1) * pb->m;
-        if (cost) cost[i] = objective_cost(pb, i, x, u);
-        if (cmax) cmax[i] = max_violation(pb, o, w, i, x, u);
+        if (cost) cost[i] = objective_cost(pb, w, i, x, u);
+        if (cmax) cmax[i] = max_violation(pb, o, i, x, u);
     }
     ws_free(w);
 }

@@ -116,6 +116,9 @@ void orc_shift_fill(const orc_problem_t *pb, int primal, int dual, double *X, do
 void orc_evaluate(const orc_problem_t *pb, const orc_opts_t *o, const double *X, const double *U,
                   double *cost, double *cmax);
 
+/* Per-iteration log [B][rows][10] (outer, iter, J, dJ, grad, rho, dV1, dV2, trials, c_max); NULL disables. */
+void orc_set_trace(double *buf, int rows);
+
 /* Unit pieces exposed for tests. */
 void orc_soc_project(int p, const double *v, double *out);
 void orc_soc_project_jac(int p, const double *v, double *J /* p*p */);

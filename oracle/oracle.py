@@ -135,6 +135,11 @@ class OracleProblem:
             raise RuntimeError(f"orc_solve_batch failed: {rc}")
         return OracleResult(pr.X.copy(), pr.U.copy(), self.lam.copy(), it, ito, st, ls, cost, cal, cmax, pmax)
 
+    def set_trace(self, rows: int):
+        self.trace = np.zeros((self.prob.B, rows, 10)) if rows else None
+        lib().orc_set_trace(_ptr(self.trace) if rows else None, rows)
+        return self.trace
+
     def shift_fill(self, primal=True, dual=True):
         pr = self.prob
         lib().orc_shift_fill(C.byref(self.c), int(primal), int(dual), _ptr(pr.X), _ptr(pr.U), _ptr(self.lam))
