@@ -289,7 +289,7 @@ class ConstraintList:
         else:
             k0, k1 = knots
         assert 0 <= k0 <= k1 <= self.N
-        self.source.append((con, (k0, k1)))
+        self.source.append((con, (k0, k1), name))
         for side, idx, G, h, sense, per_knot, per_instance in con.lower(self.n, self.m):
             kk1 = min(k1, self.N - 1) if side == CONTROL else k1  # u_N is not a decision variable
             if kk1 <= k0:
@@ -346,6 +346,26 @@ class Problem:
 
     def size(self):
         return self.n, self.m, self.N
+
+    def slice(self, i0: int, i1: int) -> "Problem":
+        """Sub-batch [i0, i1) as an independent Problem (the shard one GPU owns, sharding.shard_range)."""
+        mdl = self.model
+        if mdl.per_instance:
+            model = LinearModel(mdl.A[i0:i1].copy(), mdl.B[i0:i1].copy(), mdl.d[i0:i1].copy(), dt=mdl.dt,
+                                per_instance=True)
+        else:
+            model = LinearModel(mdl.A.copy(), mdl.B.copy(), mdl.d.copy(), dt=mdl.dt, per_instance=False)
+        cons = ConstraintList(self.n, self.m, self.N)
+        cons.source = list(self.constraints.source)
+        for c in self.constraints.flat:
+            G = c.G[i0:i1].copy() if c.per_instance else c.G.copy()
+            h = c.h[i0:i1].copy() if c.per_instance else c.h.copy()
+            cons.flat.append(FlatConstraint(c.sense, c.side, c.k0, c.k1, c.inds.copy(), G, h, c.per_knot,
+                                            c.per_instance, c.name))
+        obj = Objective(self.obj.Q, self.obj.R, self.obj.Qf, self.Xref[i0:i1], self.Uref[i0:i1])
+        p = Problem(model, obj, self.N, self.x0[i0:i1], cons, batch=i1 - i0, X0=self.X[i0:i1], U0=self.U[i0:i1])
+        p.dt = self.dt
+        return p
 
     # --- mutators (TO.set_initial_state!, TO.update_trajectory!, initial_controls!, model.A[i] = ...)
     def set_initial_state(self, x0) -> None:

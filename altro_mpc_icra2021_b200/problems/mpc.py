@@ -30,13 +30,13 @@ def gen_tracking_problem(prob: Problem, X_track: np.ndarray, U_track: np.ndarray
     Xref, Uref = window_reference(X_track, U_track, k_start, N)
     obj = TrackingObjective(np.full(n, Qk), np.full(m, Rk), Xref, Uref, Qf=np.full(n, Qfk))
     cons = ConstraintList(n, m, N)
-    for con, (k0, k1) in prob.constraints.source:
+    for con, (k0, k1), name in prob.constraints.source:
         if isinstance(con, GoalConstraint):
             continue
         if k1 > N:  # inds.start : N - (prob.N - inds.stop), mpc.jl:35-37
             k1 = N - (Nl - k1)
         if k1 > k0:
-            cons.add_constraint(con, (k0, k1))
+            cons.add_constraint(con, (k0, k1), name)
     mdl = prob.model
     model = LinearModel(mdl.A, mdl.B, mdl.d, dt=mdl.dt, per_instance=mdl.per_instance)
     return Problem(model, obj, N, x0=Xref[:, 0, :], constraints=cons, batch=batch, X0=Xref, U0=Uref)

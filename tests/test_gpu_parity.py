@@ -1,0 +1,267 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libaltro_b200.so), against the CPU
+oracle on the same seeded inputs and against the committed golden vectors.
+
+Bar: BIT-IDENTICAL FP64 trajectories, duals, costs, and identical iteration / line-search / status counts.
+(north_star asks for 1e-6 relative and equal iteration counts; AL-iLQR on conic problems is a semismooth Newton
+method whose Hessian branch at a cone boundary is decided by one ulp, so equal iteration counts are only
+guaranteed by identical arithmetic -- see DESIGN.md 'Parity contract'.)"""
+import copy
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from altro_mpc_icra2021_b200.problem import (ConstraintList, Equality, GoalConstraint, Inequality, LinearConstraint,
+                                             LinearModel, LQRObjective, Problem, SecondOrderCone, SolverOptions, CONTROL)
+from altro_mpc_icra2021_b200.problems import mpc, quadruped, random_linear, rocket
+from tests.golden import cases
+from tests.helpers import OracleSolver, assert_bit_identical, lqr_problem
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gpu_solver(prob, opts, **kw):
+    from altro_mpc_icra2021_b200.solver import ALTROSolver
+
+    return ALTROSolver(prob, opts, **kw)
+
+
+def solve_both(prob, opts, **kw):
+    pg = copy.deepcopy(prob)
+    o = OracleSolver(prob, opts).solve()
+    g = gpu_solver(pg, opts, **kw).solve()
+    assert_bit_identical(pg, g.stats, g.get_duals(), o.stats)
+    return pg, g, o
+
+
+# ------------------------------------------------------------------ golden vectors and MPC loops
+
+def test_rocket_cold_solve_golden():
+    gold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+    prob, opts = cases.rocket_track()
+    g = gpu_solver(prob, opts).solve()
+    assert np.array_equal(prob.X[0], gold["X"]) and np.array_equal(prob.U[0], gold["U"])
+    assert np.array_equal(g.stats.iterations, gold["iters"]) and g.stats.status[0] == 1
+
+
+def test_rocket_mpc_golden():
+    cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+    out = cases.run_case(gpu_solver, *cases.case_rocket_mpc(cold["X"], cold["U"]))
+    gold = np.load(os.path.join(GOLD, "rocket_mpc.npz"))
+    for k in gold.files:
+        assert np.array_equal(out[k], gold[k]), k
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_family_golden(name):
+    out = cases.run_case(gpu_solver, *cases.CASES[name]())
+    gold = np.load(os.path.join(GOLD, f"{name}.npz"))
+    for k in gold.files:
+        assert np.array_equal(out[k], gold[k]), k
+
+
+@pytest.mark.parametrize("family", ["rocket", "random_linear", "quadruped_lin", "quadruped_soc"])
+def test_mpc_loop_against_live_oracle(family):
+    """256 instances, 4 warm-started MPC steps, GPU and oracle advanced with identical host updates."""
+    B = 256
+    if family == "rocket":
+        cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+        prob, opts, steps, adv = cases.case_rocket_mpc(cold["X"], cold["U"], batch=B)
+        _, _, _, adv2 = cases.case_rocket_mpc(cold["X"], cold["U"], batch=B)
+    elif family == "random_linear":
+        prob, opts, steps, adv = cases.case_random_linear(batch=B)
+        _, _, _, adv2 = cases.case_random_linear(batch=B)
+    else:
+        prob, opts, steps, adv = cases.case_quadruped(family.endswith("lin"), batch=B)
+        _, _, _, adv2 = cases.case_quadruped(family.endswith("lin"), batch=B)
+    pg = copy.deepcopy(prob)
+    o, g = OracleSolver(prob, opts, nthreads=8), gpu_solver(pg, opts)
+    for st in range(4):
+        o.solve()
+        g.solve()
+        assert_bit_identical(pg, g.stats, g.get_duals(), o.stats, f"{family} step {st}")
+        assert np.mean(g.stats.status == 1) > 0.99
+        adv(prob, o, st)
+        adv2(pg, g, st)
+
+
+# ------------------------------------------------------------------ kernel variants
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256])
+def test_threads_per_instance_do_not_change_bits(threads):
+    prob, opts, _, _ = cases.case_quadruped(False, batch=16)
+    solve_both(prob, opts, threads_per_instance=threads)
+
+
+def test_runtime_dimension_kernel_matches_compiled_dimensions(monkeypatch):
+    prob, opts, _, _ = cases.case_random_linear(batch=8)
+    ref = copy.deepcopy(prob)
+    a = gpu_solver(ref, opts).solve()
+    monkeypatch.setenv("ALTRO_B200_GENERIC", "1")
+    gen = copy.deepcopy(prob)
+    b = gpu_solver(gen, opts).solve()
+    assert np.array_equal(ref.X, gen.X) and np.array_equal(ref.U, gen.U)
+    assert np.array_equal(a.stats.iterations, b.stats.iterations)
+
+
+@pytest.mark.parametrize("n,m,N", [(2, 2, 21), (5, 2, 9), (15, 2, 21), (30, 6, 21), (3, 1, 2)])
+def test_odd_dimensions_use_the_runtime_kernel(n, m, N):
+    solve_both(lqr_problem(n=n, m=m, N=N, batch=7, seed=n + m, u_bnd=0.4), SolverOptions(constraint_tolerance=1e-6))
+
+
+# ------------------------------------------------------------------ edge cases
+
+def test_single_instance_and_unconstrained():
+    solve_both(lqr_problem(batch=1, seed=3), SolverOptions())
+
+
+def test_empty_constraint_list_large_batch():
+    pg, g, o = solve_both(lqr_problem(n=6, m=3, N=21, batch=300, seed=4), SolverOptions())
+    assert np.all(g.stats.status == 1) and np.all(g.stats.c_max == 0.0)
+
+
+def test_goal_equality_and_state_bounds():
+    from altro_mpc_icra2021_b200.problem import BoundConstraint
+
+    prob = lqr_problem(n=4, m=2, N=15, batch=9, seed=8)
+    prob.constraints.add_constraint(GoalConstraint(np.zeros(4)), 14)
+    prob.constraints.add_constraint(BoundConstraint(4, 2, x_min=-2.0, x_max=2.0, u_min=-1.0, u_max=1.0), (1, 15))
+    opts = SolverOptions(constraint_tolerance=1e-6, penalty_initial=10.0)
+    pg, g, o = solve_both(prob, opts)
+    assert np.all(g.stats.status == 1) and np.abs(pg.X[:, -1]).max() < 1e-5
+
+
+def test_per_knot_per_instance_constraint_data_and_update():
+    """Time-varying, per-instance affine rows (the grasp benchmark's torque-balance data) and their in-place
+    update between solves (grasp_mpc_helpers.jl:46-55)."""
+    n, m, N, B = 4, 3, 10, 6
+    prob = lqr_problem(n=n, m=m, N=N, batch=B, seed=21)
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((B, N - 1, 2, m))
+    b = 0.1 * rng.standard_normal((B, N - 1, 2))
+    prob.constraints.add_constraint(LinearConstraint(n, m, A, b, Equality, ":control", per_knot=True, per_instance=True),
+                                    (0, N - 1))
+    Ac = rng.standard_normal((N - 1, 3, m))
+    Ac[:, -1] = np.abs(Ac[:, -1]) + 1.0
+    prob.constraints.add_constraint(LinearConstraint(n, m, Ac, np.zeros((N - 1, 3)) - np.array([0, 0, 1.0]),
+                                                     SecondOrderCone, ":control", per_knot=True), (0, N - 1))
+    opts = SolverOptions(constraint_tolerance=1e-5, penalty_initial=10.0, reset_duals=False)
+    pg = copy.deepcopy(prob)
+    o, g = OracleSolver(prob, opts).solve(), gpu_solver(pg, opts).solve()
+    assert_bit_identical(pg, g.stats, g.get_duals(), o.stats, "first solve")
+    for p_ in (prob, pg):
+        p_.set_constraint_data(0, h=p_.constraints.flat[0].h * 0.5)
+        p_.set_initial_state(p_.x0 * 0.9)
+    o.solve()
+    g.solve()
+    assert_bit_identical(pg, g.stats, g.get_duals(), o.stats, "after data update")
+
+
+def test_iteration_caps_and_status_codes():
+    prob, opts, _, _ = cases.case_quadruped(False, batch=12)
+    o2 = opts.copy()
+    o2.iterations = 1
+    pg, g, o = solve_both(prob, o2)
+    assert set(g.stats.status) <= {0, 1, 2}
+    prob, opts, _, _ = cases.case_quadruped(False, batch=12)
+    o3 = opts.copy()
+    o3.iterations_outer, o3.constraint_tolerance = 1, 1e-12
+    pg, g, o = solve_both(prob, o3)
+    assert np.all(g.stats.iterations_outer == 1)
+
+
+@pytest.mark.parametrize("switch", ["dj_zero_converges", "soc_hess_exact", "soc_viol_proj", "reset_duals"])
+def test_option_switches_flip_consistently(switch):
+    prob, opts, _, _ = cases.case_quadruped(False, batch=10)
+    o2 = opts.copy()
+    setattr(o2, switch, not getattr(o2, switch))
+    solve_both(prob, o2)
+
+
+# ------------------------------------------------------------------ device-side helpers of the MPC loop
+
+def test_device_mpc_transition_equals_host_update():
+    cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+    Xt, Ut = cold["X"], cold["U"]
+    B = 64
+    prob, opts, _, _ = cases.case_rocket_mpc(Xt, Ut, batch=B)
+    ks = np.zeros(B, dtype=np.int64)
+    ks[:] = mpc.rng_for(11, 0).integers(0, Xt.shape[0] - 21 - 110, size=B)  # same draw as rocket.mpc_problem
+    pg = copy.deepcopy(prob)
+    o, g = OracleSolver(prob, opts), gpu_solver(pg, opts)
+    g.set_track(Xt, Ut, ks)
+    o.solve()
+    g.solve()
+    rng = mpc.rng_for(5, 5)
+    for st in range(3):
+        nz = rocket.noise(prob.X[:, 1, :], rng)
+        ks = ks + 1
+        prob.set_initial_state(prob.X[:, 1, :] + nz)
+        prob.update_trajectory(*mpc.window_reference(Xt, Ut, ks, prob.N))
+        o.shift_fill(True, True)
+        g.mpc_transition(nz, shift=True)  # plant step + noise + reference window + shifts, all on the device
+        o.solve()
+        g.solve()
+        assert_bit_identical(pg, g.stats, g.get_duals(), o.stats, f"step {st}")
+        assert np.array_equal(pg.X[:, 0], prob.x0)
+
+
+def test_snapshot_restore_and_benchmark_solve():
+    prob, opts, _, _ = cases.case_random_linear(batch=32)
+    g = gpu_solver(prob, opts)
+    g.solve()
+    prob.set_initial_state(prob.X[:, 1, :] * 1.01)
+    g.shift_fill(True, True)
+    times = g.benchmark_solve(samples=2, evals=2)
+    X1, it1 = prob.X.copy(), g.stats.iterations.copy()
+    assert times.shape == (4,) and np.all(times > 0)
+    g._ck(g.lib.altro_restore(g.h))
+    g.solve()
+    assert np.array_equal(prob.X, X1) and np.array_equal(g.stats.iterations, it1)  # restore-and-resolve repeats
+
+
+def test_trace_matches_oracle_trace():
+    prob, opts, _, _ = cases.case_quadruped(True, batch=4)
+    pg = copy.deepcopy(prob)
+    o = OracleSolver(prob, opts, nthreads=1)
+    tro = o.op.set_trace(16)
+    o.solve()
+    o.op.set_trace(0)
+    g = gpu_solver(pg, opts)
+    g.set_trace(16)
+    g.solve()
+    trg = g.get_trace()
+    assert np.array_equal(np.nan_to_num(trg, nan=-1.0), np.nan_to_num(tro, nan=-1.0))
+
+
+# ------------------------------------------------------------------ error behaviour of the C ABI
+
+def test_abi_rejects_bad_arguments():
+    from altro_mpc_icra2021_b200 import solver as S
+
+    lib = S.load_library()
+    h = ctypes.c_void_p()
+    assert lib.altro_create(ctypes.byref(h), 0, 0, 3, 21, 4, 0.1) != 0
+    assert lib.altro_create(ctypes.byref(h), 99, 6, 3, 21, 4, 0.1) != 0
+    assert lib.altro_create(ctypes.byref(h), 0, 6, 3, 21, 4, 0.1) == 0
+    inds = np.arange(3, dtype=np.int32)
+    G, hv = np.eye(4, 3), np.zeros(4)
+    cid = ctypes.c_int()
+    add = lib.altro_add_constraint
+    assert add(h, 2, 1, 0, 21, 4, 3, S._p(inds), 0, 0, S._p(G), S._p(hv), ctypes.byref(cid)) == -1  # control block past N-1
+    assert b"knot range" in lib.altro_last_error(h)
+    bad = np.array([0, 1, 7], dtype=np.int32)
+    assert add(h, 2, 1, 0, 20, 4, 3, S._p(bad), 0, 0, S._p(G), S._p(hv), ctypes.byref(cid)) == -1
+    assert add(h, 2, 1, 0, 20, 4, 3, S._p(inds), 0, 0, S._p(G), S._p(hv), ctypes.byref(cid)) == 0 and cid.value == 0
+    assert lib.altro_solve(h) == -4 and b"dynamics and cost" in lib.altro_last_error(h)  # nothing uploaded yet
+    assert lib.altro_destroy(h) == 0
+
+
+def test_oversized_problem_is_an_error_not_a_fallback():
+    prob = lqr_problem(n=40, m=30, N=101, batch=2, seed=1)
+    from altro_mpc_icra2021_b200.solver import AltroError
+
+    with pytest.raises(AltroError, match="shared memory"):
+        gpu_solver(prob, SolverOptions()).solve()

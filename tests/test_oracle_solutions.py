@@ -1,0 +1,196 @@
+"""The oracle's solutions against independent computations: closed-form LQR (explicit Riccati in numpy),
+a bound-constrained QP solved by scipy.optimize.lsq_linear (the reference cross-checks ALTRO against OSQP the
+same way, random_linear_problem.jl:177-186), a conic problem solved by scipy SLSQP (stands in for the ECOS
+cross-check, simple_rocket.jl:184-192), KKT residuals, and the iteration statistics recovered from the
+reference's saved results."""
+import numpy as np
+import pytest
+from scipy.optimize import lsq_linear, minimize
+
+from altro_mpc_icra2021_b200.problem import SolverOptions
+from altro_mpc_icra2021_b200.problems import flexsat, mpc, quadruped, random_linear, rocket
+from oracle.oracle import OracleProblem
+from tests.helpers import OracleSolver, lqr_problem
+
+
+def riccati_lqr(prob, i):
+    """Exact finite-horizon affine LQR by the explicit Riccati recursion (independent numpy code)."""
+    n, m, N, dt = prob.n, prob.m, prob.N, prob.dt
+    A, B, d = prob.model.A, prob.model.B, prob.model.d
+    Q, R, Qf = np.diag(prob.obj.Q) * dt, np.diag(prob.obj.R) * dt, np.diag(prob.obj.Qf)
+    xr, ur = prob.Xref[i], prob.Uref[i]
+    S, s = Qf.copy(), -Qf @ xr[-1]
+    Ks, ds = [], []
+    for k in range(N - 2, -1, -1):
+        q, r = -Q @ xr[k], -R @ ur[k]
+        Sd = S @ d + s
+        Quu = R + B.T @ S @ B
+        Ks.append(-np.linalg.solve(Quu, B.T @ S @ A))
+        ds.append(-np.linalg.solve(Quu, r + B.T @ Sd))
+        K, dd = Ks[-1], ds[-1]
+        Acl = A + B @ K
+        S_new = Q + K.T @ R @ K + Acl.T @ S @ Acl
+        s = q + K.T @ (R @ dd + r) + Acl.T @ (S @ (B @ dd + d) + s)
+        S = 0.5 * (S_new + S_new.T)
+    Ks.reverse()
+    ds.reverse()
+    X = np.zeros((N, n))
+    U = np.zeros((N - 1, m))
+    X[0] = prob.x0[i]
+    for k in range(N - 1):
+        U[k] = Ks[k] @ X[k] + ds[k]
+        X[k + 1] = A @ X[k] + B @ U[k] + d
+    return X, U
+
+
+def test_unconstrained_lqr_is_one_newton_step():
+    prob = lqr_problem(n=5, m=2, N=25, batch=4, seed=1)
+    prob.Xref[...] = 0.1 * np.random.default_rng(0).standard_normal(prob.Xref.shape)
+    r = OracleProblem(prob).solve(SolverOptions())
+    assert np.all(r.status == 1) and np.all(r.iterations <= 2)  # exact after one step, second confirms
+    for i in range(prob.B):
+        X, U = riccati_lqr(prob, i)
+        assert np.allclose(r.X[i], X, rtol=1e-9, atol=1e-10) and np.allclose(r.U[i], U, rtol=1e-9, atol=1e-10)
+
+
+def condensed_qp(prob, i):
+    """min ||C u - e||^2 over stacked controls: eliminates the states of the tracking QP."""
+    n, m, N, dt = prob.n, prob.m, prob.N, prob.dt
+    A, B, d = prob.model.A, prob.model.B, prob.model.d
+    Phi = np.zeros((N, n, (N - 1) * m))
+    free = np.zeros((N, n))
+    free[0] = prob.x0[i]
+    for k in range(N - 1):
+        Phi[k + 1] = A @ Phi[k]
+        Phi[k + 1][:, k * m:(k + 1) * m] += B
+        free[k + 1] = A @ free[k] + d
+    rows, rhs = [], []
+    for k in range(N):
+        w = np.sqrt(prob.obj.Qf if k == N - 1 else prob.obj.Q * dt)
+        rows.append(w[:, None] * Phi[k])
+        rhs.append(w * (prob.Xref[i, k] - free[k]))
+    for k in range(N - 1):
+        w = np.sqrt(prob.obj.R * dt)
+        E = np.zeros((m, (N - 1) * m))
+        E[:, k * m:(k + 1) * m] = np.diag(w)
+        rows.append(E)
+        rhs.append(w * prob.Uref[i, k])
+    return np.vstack(rows), np.concatenate(rhs)
+
+
+def test_bound_constrained_qp_matches_lsq_linear():
+    prob = lqr_problem(n=4, m=2, N=12, batch=3, seed=5, u_bnd=0.3)
+    opts = SolverOptions(constraint_tolerance=1e-8, cost_tolerance=1e-10, cost_tolerance_intermediate=1e-10,
+                         penalty_initial=10.0, penalty_scaling=10.0)
+    r = OracleProblem(prob).solve(opts)
+    assert np.all(r.status == 1)
+    active = 0
+    for i in range(prob.B):
+        C, e = condensed_qp(prob, i)
+        ref = lsq_linear(C, e, bounds=(-0.3, 0.3), method="bvls", tol=1e-14)
+        assert np.allclose(r.U[i].ravel(), ref.x, atol=2e-6), np.abs(r.U[i].ravel() - ref.x).max()
+        active += int(np.sum(np.abs(np.abs(ref.x) - 0.3) < 1e-9))
+    assert active > 5, "test problem should have active bounds"
+
+
+def test_kkt_residuals_bound_qp():
+    """Stationarity of the Lagrangian with the solver's own multipliers, primal/dual feasibility,
+    complementarity -- solver-independent optimality certificate."""
+    prob = lqr_problem(n=4, m=2, N=12, batch=3, seed=5, u_bnd=0.3)
+    opts = SolverOptions(constraint_tolerance=1e-8, cost_tolerance=1e-10, cost_tolerance_intermediate=1e-10,
+                         penalty_initial=10.0, penalty_scaling=10.0)
+    op = OracleProblem(prob)
+    r = op.solve(opts)
+    con = prob.constraints.flat[0]
+    for i in range(prob.B):
+        C, e = condensed_qp(prob, i)
+        u = r.U[i].ravel()
+        lam = r.lam[i].reshape(prob.N - 1, con.p)
+        g = C.T @ (C @ u - e)
+        gc = np.zeros_like(r.U[i])
+        for k in range(prob.N - 1):
+            gc[k, con.inds] += con.G.T @ lam[k]
+        assert np.abs(g + gc.ravel()).max() < 1e-5  # stationarity
+        cv = np.array([con.G @ r.U[i, k, con.inds] + con.h for k in range(prob.N - 1)])
+        assert cv.max() < 1e-7 and lam.min() >= 0.0 and np.abs(lam * cv).max() < 1e-5
+
+
+def test_soc_problem_matches_slsqp():
+    """Rocket-style MPC instance (3 second-order cones) against scipy SLSQP on the condensed problem."""
+    cold = rocket.cold_problem()
+    rc = OracleProblem(cold).solve(rocket.cold_options())
+    assert rc.status[0] == 1
+    pm, _ = rocket.mpc_problem(cold, rc.X[0], rc.U[0], 11, batch=1)
+    rng = np.random.default_rng(0)
+    pm.set_initial_state(pm.x0 + np.array([0.3, -0.2, 0.1, 0.05, 0.05, -0.05]))
+    opts = rocket.mpc_options()
+    opts.constraint_tolerance = 1e-7
+    opts.cost_tolerance = opts.cost_tolerance_intermediate = 1e-9
+    r = OracleProblem(pm).solve(opts)
+    assert r.status[0] == 1
+    A, B, d = pm.model.A, pm.model.B, pm.model.d
+    N, n, m = pm.N, pm.n, pm.m
+
+    def rollout(u):
+        U = u.reshape(N - 1, m)
+        X = np.zeros((N, n))
+        X[0] = pm.x0[0]
+        for k in range(N - 1):
+            X[k + 1] = A @ X[k] + B @ U[k] + d
+        return X, U
+
+    def cost(u):
+        X, U = rollout(u)
+        return pm.dt * (0.5 * np.sum(pm.obj.Q * (X[:-1] - pm.Xref[0, :-1]) ** 2)
+                        + 0.5 * np.sum(pm.obj.R * (U - pm.Uref[0]) ** 2)) + 0.5 * np.sum(
+            pm.obj.Qf * (X[-1] - pm.Xref[0, -1]) ** 2)
+
+    def margins(u):  # >= 0 when feasible
+        X, U = rollout(u)
+        out = []
+        for c in pm.constraints.flat:
+            for k in range(c.k0, c.k1):
+                cv = c.G @ (X[k] if c.side == 0 else U[k])[c.inds] + c.h
+                out.append(cv[-1] - np.sqrt(np.sum(cv[:-1] ** 2) + 1e-16))
+        return np.array(out)
+
+    ref = minimize(cost, pm.Uref[0].ravel(), method="SLSQP", constraints=[{"type": "ineq", "fun": margins}],
+                   options=dict(ftol=1e-14, maxiter=500))
+    assert ref.success
+    assert abs(cost(r.U[0].ravel()) - ref.fun) <= 1e-6 * max(1.0, abs(ref.fun))
+    assert np.abs(r.U[0].ravel() - ref.x).max() < 5e-4 * max(1.0, np.abs(ref.x).max())
+    assert margins(r.U[0].ravel()).min() > -1e-6
+
+
+def test_random_linear_iteration_statistics_match_reference_data():
+    """Saved reference runs: 2 iLQR iterations in 92-100 % of warm-started MPC steps, never 1 after the
+    first step, never more than 5 (horizon_comp.jld2 etc.)."""
+    pm, X, U, ks = random_linear.mpc_problem(12, 6, 21, batch=1)
+    s = OracleSolver(pm, random_linear.mpc_options(), nthreads=1)
+    s.solve()
+    loop = mpc.MPCLoop(s, X, U, ks, noise=random_linear.noise)
+    its = []
+    for _ in range(100):
+        loop.step()
+        assert s.stats.status[0] == 1
+        its.append(int(s.stats.iterations[0]))
+    its = np.array(its)
+    assert np.mean(its == 2) >= 0.92 and its.min() >= 2 and its.max() <= 5, np.bincount(its)
+
+
+@pytest.mark.parametrize("family", ["quadruped_lin", "quadruped_soc", "flexsat"])
+def test_families_converge_and_are_feasible(family):
+    if family == "flexsat":
+        prob, opts = flexsat.mpc_problem(40, batch=4), flexsat.mpc_options()
+    else:
+        prob, _ = quadruped.mpc_problem(8, linearized_friction=(family == "quadruped_lin"))
+        opts = quadruped.mpc_options()
+    op = OracleProblem(prob)
+    r = op.solve(opts, nthreads=4)
+    assert np.all(r.status == 1) and np.all(r.c_max < opts.constraint_tolerance)
+    cost, cmax = op.evaluate(opts)
+    assert np.array_equal(cost, r.cost) and np.array_equal(cmax, r.c_max)
+    if family.startswith("quadruped"):  # reference's own feasibility check: mujoco_test.jl:185-206, eps = 1e-4
+        f = r.U.reshape(prob.B, prob.N - 1, 4, 3)
+        assert np.all(f[..., 2] >= -1e-4) and np.all(f[..., 2] <= 133 + 1e-4)
+        assert np.all(np.abs(f[..., 0]) <= 0.5 * f[..., 2] + 1e-4) and np.all(np.abs(f[..., 1]) <= 0.5 * f[..., 2] + 1e-4)
