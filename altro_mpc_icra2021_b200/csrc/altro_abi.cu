@@ -60,9 +60,10 @@ struct altro_handle_s {
     int P = 0, EX = 0;
     bool finalized = false, have_dyn = false, have_cost = false, have_ref = false, have_x0 = false;
     // MPC track
-    double *trackX = nullptr, *trackU = nullptr, *noise = nullptr;
+    double *trackX = nullptr, *trackU = nullptr, *noise = nullptr, *noise_bank = nullptr;
     int *kidx = nullptr;
-    int Nt = 0;
+    int Nt = 0, bank_steps = 0, bank_pos = 0, noise_mode = 0;
+    double noise_w1 = 1.0, noise_w2 = 1.0;
     // launch
     int threads_req = 0, threads = 0, smem = 0, regs = 0, ctas_per_sm = 0, num_sms = 0, dyn_in_smem = 0, ref_in_smem = 1;
     const void *kernel = nullptr;
@@ -124,21 +125,46 @@ __global__ void shift_fill_kernel(int n, int m, int N, int P, int ncon, const Co
 
 // Device-side MPC transition (random_linear_problem.jl:121-139, simple_rocket.jl:59-82):
 // plant step with the first control (+ noise), reference window advanced along the track.
+// Noise models: 0 additive w1*z; 1 random-linear z*|x|_inf*w1 (random_linear_problem.jl:129);
+// 2 rocket: z*|x[0:n/2]|_2*w1 on positions, z*|x[n/2:n]|_2*w2 on velocities (simple_rocket.jl:63-70).
 __global__ void mpc_transition_kernel(int n, int m, int N, const double *A, const double *Bm, const double *d,
                                       int dyn_per_knot, int dyn_per_instance, const double *X, const double *U,
-                                      const double *noise, double *x0, const double *trackX, const double *trackU,
-                                      int Nt, int *kidx, double *xref, double *uref)
+                                      const double *noise, int noise_mode, double w1, double w2, double *x0,
+                                      const double *trackX, const double *trackU, int Nt, int *kidx, double *xref,
+                                      double *uref)
 {
+    __shared__ double scale[2];
     const int inst = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const size_t base = dyn_per_instance ? (size_t)inst * (dyn_per_knot ? (size_t)(N - 1) : 1) : 0;
     const double *A0 = A + base * n * n, *B0 = Bm + base * n * m, *d0 = d + base * n;
     const double *x = X + (size_t)inst * N * n, *u = U + (size_t)inst * (N - 1) * m;
+    double *xo = x0 + (size_t)inst * n;
     for (int i = tid; i < n; i += T) {
         double acc = d0[i];
         for (int j = 0; j < n; ++j) acc = fma(A0[i * n + j], x[j], acc);
         for (int j = 0; j < m; ++j) acc = fma(B0[i * m + j], u[j], acc);
-        if (noise) acc += noise[(size_t)inst * n + i];
-        x0[(size_t)inst * n + i] = acc;
+        xo[i] = acc;
+    }
+    __syncthreads();
+    if (noise) {
+        if (tid == 0) {
+            double s0 = w1, s1 = w1;
+            if (noise_mode == 1) {
+                double mx = 0.0;
+                for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(xo[i]));
+                s0 = s1 = mx * w1;
+            } else if (noise_mode == 2) {
+                double a = 0.0, b = 0.0;
+                for (int i = 0; i < n / 2; ++i) a += xo[i] * xo[i];
+                for (int i = n / 2; i < n; ++i) b += xo[i] * xo[i];
+                s0 = sqrt(a) * w1;
+                s1 = sqrt(b) * w2;
+            }
+            scale[0] = s0;
+            scale[1] = s1;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += T) xo[i] += noise[(size_t)inst * n + i] * scale[(noise_mode == 2 && i >= n / 2) ? 1 : 0];
     }
     if (trackX) {
         const int k0 = kidx[inst] + 1;
@@ -389,7 +415,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->trace, h->con_dev, h->trackX, h->trackU, h->noise, h->kidx};
+                    h->penmax, h->t_ns, h->trace, h->con_dev, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -746,17 +772,52 @@ int altro_set_track(altro_handle_t h, const double *tX, const double *tU, int Nt
     return ALTRO_OK;
 }
 
+int altro_set_noise_model(altro_handle_t h, int mode, double w1, double w2)
+{
+    REQ(h);
+    if (mode < 0 || mode > 2) return fail(h, ALTRO_ERR_INVALID, "noise mode must be 0, 1 or 2");
+    h->noise_mode = mode; h->noise_w1 = w1; h->noise_w2 = w2;
+    return ALTRO_OK;
+}
+
+int altro_get_x0(altro_handle_t h, double *x0)
+{
+    REQ(h);
+    int rc = download(h, x0, h->x0, (size_t)h->B * h->n * sizeof(double));
+    if (!rc) CK(h, cudaStreamSynchronize(h->stream));
+    return rc;
+}
+
+int altro_set_noise_bank(altro_handle_t h, const double *noise, int steps)
+{
+    REQ(h);
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->noise_bank) { cudaFree(h->noise_bank); h->noise_bank = nullptr; }
+    h->bank_steps = h->bank_pos = 0;
+    if (!noise || steps < 1) return ALTRO_OK;
+    const size_t cnt = (size_t)steps * h->B * h->n;
+    CK(h, dalloc(&h->noise_bank, cnt));
+    CK(h, cudaMemcpy(h->noise_bank, noise, cnt * sizeof(double), cudaMemcpyHostToDevice));
+    h->bank_steps = steps;
+    return ALTRO_OK;
+}
+
 int altro_mpc_transition(altro_handle_t h, const double *noise, int shift)
 {
     REQ(h);
     int rc = finalize(h);
     if (rc) return rc;
+    const double *nz = nullptr;
     if (noise) {
         rc = upload(h, h->noise, noise, (size_t)h->B * h->n);
         if (rc) return rc;
+        nz = h->noise;
+    } else if (h->noise_bank) {  // device-resident noise: no host traffic at all
+        nz = h->noise_bank + (size_t)(h->bank_pos % h->bank_steps) * h->B * h->n;
+        ++h->bank_pos;
     }
     mpc_transition_kernel<<<h->B, 64, 0, h->stream>>>(h->n, h->m, h->N, h->A, h->Bm, h->d, h->dyn_per_knot,
-                                                     h->dyn_per_instance, h->X, h->U, noise ? h->noise : nullptr,
+                                                     h->dyn_per_instance, h->X, h->U, nz, h->noise_mode, h->noise_w1, h->noise_w2,
                                                      h->x0, h->trackX, h->trackU, h->Nt, h->kidx, h->xref, h->uref);
     CK(h, cudaGetLastError());
     h->have_x0 = true;

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "altro_set_options", "altro_set_dynamics", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint",
     "altro_update_constraint_data", "altro_set_x0", "altro_set_trajectory", "altro_get_trajectory", "altro_dual_len",
     "altro_set_duals", "altro_get_duals", "altro_shift_fill", "altro_solve", "altro_sync", "altro_get_stats",
-    "altro_get_timing", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition",
+    "altro_get_timing", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0",
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
     "altro_measure_peaks",
 ]
@@ -257,6 +257,24 @@ class ALTROSolver:
         Ut = np.ascontiguousarray(U_track, dtype=np.float64)
         ks = np.ascontiguousarray(k_start, dtype=np.int32)
         self._ck(self.lib.altro_set_track(self.h, _p(Xt), _p(Ut), Xt.shape[0], _p(ks)))
+
+    def set_noise_model(self, mode: int, w1: float = 1.0, w2: float = 1.0) -> None:
+        """0 additive, 1 random-linear (|x|_inf relative), 2 rocket (position / velocity 2-norm relative)."""
+        self._ck(self.lib.altro_set_noise_model(self.h, int(mode), C.c_double(w1), C.c_double(w2)))
+
+    def get_x0(self) -> np.ndarray:
+        x0 = np.zeros((self.prob.B, self.prob.n))
+        self._ck(self.lib.altro_get_x0(self.h, _p(x0)))
+        return x0
+
+    def set_noise_bank(self, noise: Optional[np.ndarray]) -> None:
+        """Device-resident process noise [steps][B][n], consumed in turn by mpc_transition(noise=None)."""
+        if noise is None:
+            self._ck(self.lib.altro_set_noise_bank(self.h, None, 0))
+            return
+        nz = np.ascontiguousarray(noise, dtype=np.float64)
+        assert nz.shape[1:] == (self.prob.B, self.prob.n)
+        self._ck(self.lib.altro_set_noise_bank(self.h, _p(nz), nz.shape[0]))
 
     def mpc_transition(self, noise: Optional[np.ndarray] = None, shift: bool = True) -> None:
         """Device-side MPC step: plant step with the first control (+ noise), reference window advance

@@ -145,6 +145,14 @@ int altro_restore(altro_handle_t h);
  * then primal + dual shift_fill.  Registers the track with altro_set_track. */
 int altro_set_track(altro_handle_t h, const double *track_X, const double *track_U, int Nt, const int *k_start);
 int altro_mpc_transition(altro_handle_t h, const double *noise /* host [B][n] or NULL */, int shift);
+/* How the noise sample z is applied to the propagated state x (the reference's per-benchmark formulas):
+ * 0: x += w1*z;  1: x += z*|x|_inf*w1 (random_linear_problem.jl:129);
+ * 2: positions x[0:n/2] += z*|x[0:n/2]|_2*w1, velocities x[n/2:n] += z*|x[n/2:n]|_2*w2 (simple_rocket.jl:63-70). */
+int altro_set_noise_model(altro_handle_t h, int mode, double w1, double w2);
+int altro_get_x0(altro_handle_t h, double *x0);
+/* Optional device-resident noise for `steps` transitions, noise[steps][B][n]: used in turn (cyclically)
+ * whenever altro_mpc_transition is called with noise == NULL, so a closed-loop run has no host traffic. */
+int altro_set_noise_bank(altro_handle_t h, const double *noise, int steps);
 
 /* Pin / unpin a caller buffer so setters and getters DMA directly (cudaHostRegister). */
 int altro_host_register(void *ptr, size_t bytes);
