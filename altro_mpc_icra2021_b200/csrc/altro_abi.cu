@@ -52,6 +52,8 @@ struct altro_handle_s {
     int *iters = nullptr, *outer = nullptr, *status = nullptr, *trials = nullptr;
     double *cost = nullptr, *cost_al = nullptr, *cmax = nullptr, *penmax = nullptr;
     long long *t_ns = nullptr;
+    int stat_cap = 1;  // statistics arrays hold stat_cap x B entries (one slot per step of a closed-loop run)
+    double *x0_log = nullptr, *u0_log = nullptr;
     double *trace = nullptr;
     int trace_rows = 0;
     // constraints
@@ -180,6 +182,12 @@ __global__ void mpc_transition_kernel(int n, int m, int N, const double *A, cons
             ur[i] = trackU[(size_t)k * m + i % m];
         }
     }
+}
+
+__global__ void advance_kidx_kernel(int *kidx, int B, int steps)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) kidx[i] += steps;
 }
 
 // ------------------------------------------------------------------ FP64 peak microbenchmarks
@@ -415,7 +423,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->trace, h->con_dev, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->trace, h->con_dev, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -638,12 +646,28 @@ int altro_shift_fill(altro_handle_t h, int primal, int dual)
     return ALTRO_OK;
 }
 
-int altro_solve(altro_handle_t h)
+static int ensure_stat_capacity(altro_handle_t h, int slots)
 {
-    REQ(h);
-    int rc = finalize(h);
-    if (rc) return rc;
-    if (!h->have_x0) return fail(h, ALTRO_ERR_STATE, "x0 not set");
+    if (slots <= h->stat_cap) return ALTRO_OK;
+    CK(h, cudaStreamSynchronize(h->stream));
+    const size_t cnt = (size_t)slots * h->B;
+    int **ip[] = {&h->iters, &h->outer, &h->status, &h->trials};
+    double **dp[] = {&h->cost, &h->cost_al, &h->cmax, &h->penmax};
+    for (auto p : ip) { cudaFree(*p); *p = nullptr; CK(h, dalloc(p, cnt)); }
+    for (auto p : dp) { cudaFree(*p); *p = nullptr; CK(h, dalloc(p, cnt)); }
+    cudaFree(h->t_ns); h->t_ns = nullptr;
+    CK(h, dalloc(&h->t_ns, cnt));
+    if (h->x0_log) cudaFree(h->x0_log);
+    if (h->u0_log) cudaFree(h->u0_log);
+    h->x0_log = h->u0_log = nullptr;
+    CK(h, dalloc(&h->x0_log, cnt * h->n));
+    CK(h, dalloc(&h->u0_log, cnt * h->m));
+    h->stat_cap = slots;
+    return ALTRO_OK;
+}
+
+static int launch_solve(altro_handle_t h, int steps, int shift)
+{
     Params P;
     memset(&P, 0, sizeof(P));
     P.n = h->n; P.m = h->m; P.N = h->N; P.B = h->B; P.P = h->P; P.ncon = (int)h->cons.size(); P.EX = h->EX;
@@ -661,12 +685,73 @@ int altro_solve(altro_handle_t h)
     P.trace_rows = h->trace_rows;
     P.con = h->con_dev;
     P.o = h->opts;
+    P.steps = steps; P.shift = shift; P.noise_mode = h->noise_mode; P.Nt = h->Nt;
+    P.noise_w1 = h->noise_w1; P.noise_w2 = h->noise_w2;
+    if (steps > 0) {
+        if (h->noise_bank) {
+            if (steps > h->bank_steps) return fail(h, ALTRO_ERR_INVALID, "noise bank holds fewer steps than requested");
+            if (h->bank_pos % h->bank_steps + steps > h->bank_steps) h->bank_pos = 0;  // keep one run contiguous
+            P.noise = h->noise_bank + (size_t)(h->bank_pos % h->bank_steps) * h->B * h->n;
+            h->bank_pos += steps;
+        }
+        P.trackX = h->trackX; P.trackU = h->trackU; P.kidx = h->kidx;
+        P.x0_log = h->x0_log; P.u0_log = h->u0_log;
+    }
     void *args[] = {&P};
     if (h->trace)
         CK(h, cudaMemsetAsync(h->trace, 0, (size_t)h->B * h->trace_rows * TRACE_COLS * sizeof(double), h->stream));
     CK(h, cudaEventRecord(h->ev0, h->stream));
     CK(h, cudaLaunchKernel(h->kernel, dim3(h->B), dim3(h->threads), args, (size_t)h->smem, h->stream));
     CK(h, cudaEventRecord(h->ev1, h->stream));
+    if (steps > 0 && h->trackX) {
+        advance_kidx_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->kidx, h->B, steps);
+        CK(h, cudaGetLastError());
+    }
+    return ALTRO_OK;
+}
+
+int altro_solve(altro_handle_t h)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (!h->have_x0) return fail(h, ALTRO_ERR_STATE, "x0 not set");
+    return launch_solve(h, 0, 0);
+}
+
+int altro_mpc_run(altro_handle_t h, int steps, int shift)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (steps < 1) return fail(h, ALTRO_ERR_INVALID, "steps must be >= 1");
+    if (!h->ref_in_smem && h->trackX)
+        return fail(h, ALTRO_ERR_UNSUPPORTED, "closed-loop runs need the reference window in shared memory (horizon too long)");
+    rc = ensure_stat_capacity(h, steps);
+    if (rc) return rc;
+    h->have_x0 = true;
+    return launch_solve(h, steps, shift);
+}
+
+int altro_get_run_results(altro_handle_t h, int steps, int *iterations, int *iterations_outer, int *status,
+                          int *ls_trials, double *cost, double *c_max, double *x0_log, double *u0_log,
+                          long long *t_ns)
+{
+    REQ(h);
+    if (steps < 1 || steps > h->stat_cap) return fail(h, ALTRO_ERR_INVALID, "steps exceeds the last run");
+    const size_t cnt = (size_t)steps * h->B;
+    int rc = ALTRO_OK;
+    if (iterations) rc |= download(h, iterations, h->iters, cnt * sizeof(int));
+    if (iterations_outer) rc |= download(h, iterations_outer, h->outer, cnt * sizeof(int));
+    if (status) rc |= download(h, status, h->status, cnt * sizeof(int));
+    if (ls_trials) rc |= download(h, ls_trials, h->trials, cnt * sizeof(int));
+    if (cost) rc |= download(h, cost, h->cost, cnt * sizeof(double));
+    if (c_max) rc |= download(h, c_max, h->cmax, cnt * sizeof(double));
+    if (x0_log && h->x0_log) rc |= download(h, x0_log, h->x0_log, cnt * h->n * sizeof(double));
+    if (u0_log && h->u0_log) rc |= download(h, u0_log, h->u0_log, cnt * h->m * sizeof(double));
+    if (t_ns) rc |= download(h, t_ns, h->t_ns, cnt * sizeof(long long));
+    if (rc) return ALTRO_ERR_CUDA;
+    CK(h, cudaStreamSynchronize(h->stream));
     return ALTRO_OK;
 }
 

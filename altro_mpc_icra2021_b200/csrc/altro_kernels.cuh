@@ -45,13 +45,19 @@ struct Params {
     int dyn_per_knot, dyn_per_instance, dyn_in_smem, ref_in_smem;
     const double *A, *Bm, *d;
     const double *Q, *R, *Qf;
-    const double *xref, *uref, *x0;
-    double *X, *U, *lam;
+    double *xref, *uref, *x0, *X, *U, *lam;
     int *iters, *outer, *status, *trials;
     double *cost, *cost_al, *cmax, *penmax;
     long long *t_ns;
     double *trace;  // optional [B][trace_rows][TRACE_COLS] per-iteration log (verbose mode), or nullptr
     int trace_rows;
+    // closed-loop MPC run: `steps` x {transition; solve!} per instance inside one launch (0 = one plain solve!)
+    int steps, shift, noise_mode, Nt;
+    double noise_w1, noise_w2;
+    const double *noise;            // [steps][B][n] standard-normal samples, or nullptr
+    const double *trackX, *trackU;  // reference track [Nt][n], [Nt-1][m], or nullptr
+    const int *kidx;                // per-instance track index of the current window start
+    double *x0_log, *u0_log;        // [steps][B][n], [steps][B][m]: closed-loop state and applied control
     const ConDesc *con;
     altro_opts_t o;
 };
@@ -161,8 +167,8 @@ struct Ctx {
         Ub = q; q += (N - 1) * m;
         if (P.ref_in_smem) { xr = q; q += N * n; ur = q; q += (N - 1) * m; }
         else {  // large horizons: read the reference through L1/L2 instead
-            xr = const_cast<double *>(P.xref) + (size_t)inst * N * n;
-            ur = const_cast<double *>(P.uref) + (size_t)inst * (N - 1) * m;
+            xr = P.xref + (size_t)inst * N * n;
+            ur = P.uref + (size_t)inst * (N - 1) * m;
         }
         K = q; q += (N - 1) * m * n;
         dv = q; q += (N - 1) * m;
@@ -220,8 +226,13 @@ struct Ctx {
             for (int i = tid; i < n * m; i += T) sB[i] = P.Bm[i];
             for (int i = tid; i < n; i += T) sd[i] = P.d[i];
         }
-        const double *gx0 = P.x0 + (size_t)inst * n;
-        for (int i = tid; i < n; i += T) X[i] = gx0[i];
+        if (P.steps > 0) {  // closed-loop run: start from the previous solution (its x_1 is the next x_0)
+            const double *gX = P.X + (size_t)inst * N * n;
+            for (int i = tid; i < N * n; i += T) X[i] = gX[i];
+        } else {
+            const double *gx0 = P.x0 + (size_t)inst * n;
+            for (int i = tid; i < n; i += T) X[i] = gx0[i];
+        }
         const double *gU = P.U + (size_t)inst * (N - 1) * m;
         for (int i = tid; i < (N - 1) * m; i += T) U[i] = gU[i];
         const double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
@@ -247,6 +258,14 @@ struct Ctx {
         for (int i = tid; i < (N - 1) * m; i += T) gU[i] = U[i];
         double *gl = P.lam + (size_t)inst * P.P;
         for (int i = tid; i < P.P; i += T) gl[i] = lam[i];
+        if (P.steps > 0) {  // closed-loop run: the handle's x0 and reference window follow the plant
+            for (int i = tid; i < n; i += T) P.x0[(size_t)inst * n + i] = X[i];
+            if (P.trackX && P.ref_in_smem) {
+                double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
+                for (int i = tid; i < N * n; i += T) gxr[i] = xr[i];
+                for (int i = tid; i < (N - 1) * m; i += T) gur[i] = ur[i];
+            }
+        }
     }
 
     // ---------------------------------------------------------------- constraint values
@@ -801,11 +820,67 @@ struct Ctx {
     }
 
     // ---------------------------------------------------------------- solve! (A.4 - A.6)
-    __device__ void solve()
+    // Warm-started MPC transition in shared memory (random_linear_problem.jl:121-139, simple_rocket.jl:59-82):
+    // x0 <- x_1 of the last solution (= plant step with its first control) + noise, reference window advanced
+    // along the track, RD.shift_fill!(Z) on the controls and Altro.shift_fill!(conSet) on the duals.
+    __device__ void transition(int st)
     {
-        long long t0 = 0;
-        if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        load();
+        const double *z = P.noise ? P.noise + ((size_t)st * P.B + inst) * n : nullptr;
+        if (z && tid == 0) {
+            const double *xo = X + n;
+            double s0 = P.noise_w1, s1 = P.noise_w1;
+            if (P.noise_mode == 1) {
+                double mx = 0.0;
+                for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(xo[i]));
+                s0 = s1 = mx * P.noise_w1;
+            } else if (P.noise_mode == 2) {
+                double a = 0.0, b = 0.0;
+                for (int i = 0; i < n / 2; ++i) a += xo[i] * xo[i];
+                for (int i = n / 2; i < n; ++i) b += xo[i] * xo[i];
+                s0 = sqrt(a) * P.noise_w1;
+                s1 = sqrt(b) * P.noise_w2;
+            }
+            bc[3] = s0;
+            bc[4] = s1;
+        }
+        gsync<T>();
+        for (int i = tid; i < n; i += T) {
+            double v = X[n + i];
+            if (z) v += z[i] * bc[(P.noise_mode == 2 && i >= n / 2) ? 4 : 3];
+            X[i] = v;
+        }
+        if (P.trackX) {
+            const int k0 = P.kidx[inst] + st + 1;
+            for (int i = tid; i < N * n; i += T) xr[i] = P.trackX[(size_t)min(k0 + i / n, P.Nt - 1) * n + i % n];
+            for (int i = tid; i < (N - 1) * m; i += T) ur[i] = P.trackU[(size_t)min(k0 + i / m, P.Nt - 2) * m + i % m];
+        }
+        if (P.shift) {
+            // in-place left shifts in chunks of T: all reads of a chunk precede its writes, later chunks are untouched
+            for (int base = 0; base < (N - 2) * m; base += T) {
+                const int i = base + tid;
+                double v = (i < (N - 2) * m) ? U[i + m] : 0.0;
+                gsync<T>();
+                if (i < (N - 2) * m) U[i] = v;
+                gsync<T>();
+            }
+            for (int ci = 0; ci < ncon; ++ci) {
+                const int cnt = (cd[ci].k1 - cd[ci].k0 - 1) * cd[ci].p, p = cd[ci].p;
+                double *l = lam + cd[ci].dual_off;
+                for (int base = 0; base < cnt; base += T) {
+                    const int i = base + tid;
+                    double v = (i < cnt) ? l[i + p] : 0.0;
+                    gsync<T>();
+                    if (i < cnt) l[i] = v;
+                    gsync<T>();
+                }
+            }
+        }
+        gsync<T>();
+    }
+
+    // ---------------------------------------------------------------- solve! (A.4 - A.6)
+    __device__ void solve_core(int slot)
+    {
         const altro_opts_t &o = P.o;
         int iters = 0, outer_done = 0, status = ALTRO_UNSOLVED, trials = 0;
         double cmax = INFINITY, J = 0.0, pen_max = 0.0;
@@ -857,22 +932,48 @@ struct Ctx {
         if (status <= ALTRO_SOLVE_SUCCEEDED)
             status = (cmax < o.constraint_tolerance) ? ALTRO_SOLVE_SUCCEEDED : ALTRO_UNSOLVED;
         double Jobj = objective_cost();
-        store();
         if (tid == 0) {
-            P.iters[inst] = iters;
-            P.outer[inst] = outer_done;
-            P.status[inst] = status;
-            P.trials[inst] = trials;
-            P.cost[inst] = Jobj;
-            P.cost_al[inst] = J;
-            P.cmax[inst] = cmax;
-            P.penmax[inst] = pen_max;
-            if (P.t_ns) {
+            const size_t at = (size_t)slot * P.B + inst;
+            P.iters[at] = iters;
+            P.outer[at] = outer_done;
+            P.status[at] = status;
+            P.trials[at] = trials;
+            P.cost[at] = Jobj;
+            P.cost_al[at] = J;
+            P.cmax[at] = cmax;
+            P.penmax[at] = pen_max;
+        }
+    }
+
+    __device__ void solve()
+    {
+        long long t0 = 0;
+        if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        load();
+        const int steps = P.steps > 0 ? P.steps : 1;
+        for (int st = 0; st < steps; ++st) {
+            if (P.steps > 0) {
+                transition(st);
+                if (st > 0) {  // every solve! starts from reset penalties (and duals, if asked)
+                    if (P.o.reset_duals)
+                        for (int i = tid; i < P.P; i += T) lam[i] = 0.0;
+                    for (int i = tid; i < MAX_CON; i += T) mu[i] = P.o.penalty_initial;
+                    gsync<T>();
+                }
+                if (P.x0_log)
+                    for (int i = tid; i < n; i += T) P.x0_log[((size_t)st * P.B + inst) * n + i] = X[i];
+            }
+            solve_core(st);
+            if (P.steps > 0 && P.u0_log)
+                for (int i = tid; i < m; i += T) P.u0_log[((size_t)st * P.B + inst) * m + i] = U[i];
+            if (tid == 0 && P.t_ns) {
                 long long t1v;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1v));
-                P.t_ns[inst] = t1v - t0;
+                P.t_ns[(size_t)st * P.B + inst] = t1v - t0;
+                t0 = t1v;
             }
         }
+        store();
     }
 };
 

@@ -33,7 +33,8 @@ ABI_SYMBOLS = [
     "altro_set_options", "altro_set_dynamics", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint",
     "altro_update_constraint_data", "altro_set_x0", "altro_set_trajectory", "altro_get_trajectory", "altro_dual_len",
     "altro_set_duals", "altro_get_duals", "altro_shift_fill", "altro_solve", "altro_sync", "altro_get_stats",
-    "altro_get_timing", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0",
+    "altro_get_timing", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0", "altro_mpc_run",
+    "altro_get_run_results",
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
     "altro_measure_peaks",
 ]
@@ -282,6 +283,26 @@ class ALTROSolver:
         self.upload()
         nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
         self._ck(self.lib.altro_mpc_transition(self.h, _p(nz), int(shift)))
+
+    def mpc_run(self, steps: int, shift: bool = True, fetch: bool = True):
+        """Closed-loop MPC run on the device: `steps` x {transition; solve!} per instance in one launch.
+        Returns a dict of per-step results (see altro_mpc_run) when fetch=True."""
+        self.upload()
+        self._ck(self.lib.altro_mpc_run(self.h, int(steps), int(shift)))
+        self._results_stale = True
+        return self.run_results(steps) if fetch else None
+
+    def run_results(self, steps: int) -> dict:
+        p, B = self.prob, self.prob.B
+        it, ito, st, ls = (np.zeros((steps, B), np.int32) for _ in range(4))
+        cost, cmax = np.zeros((steps, B)), np.zeros((steps, B))
+        x0l, u0l, tns = np.zeros((steps, B, p.n)), np.zeros((steps, B, p.m)), np.zeros((steps, B), np.int64)
+        self._ck(self.lib.altro_get_run_results(self.h, steps, _p(it), _p(ito), _p(st), _p(ls), _p(cost), _p(cmax),
+                                                _p(x0l), _p(u0l), _p(tns)))
+        self._ck(self.lib.altro_get_trajectory(self.h, _p(p.X), _p(p.U)))
+        p.x0[...] = x0l[-1]
+        return {"iterations": it, "iterations_outer": ito, "status": st, "ls_trials": ls, "cost": cost, "c_max": cmax,
+                "x0": x0l, "u0": u0l, "t_us": tns / 1e3, "device_ms": self.device_ms()}
 
     # ------------------------------------------------------------------ queries
     def states(self) -> np.ndarray:

@@ -178,32 +178,40 @@ def host_threads():
 
 def oracle_arm(wl: Workload, steps, warmup, nthreads):
     """Times the CPU oracle (port of the reference algorithm) on the same workload with `nthreads` host threads.
-    The one place besides tests/ and smoke() that executes oracle/ -- as the measured CPU baseline only."""
+    The one place besides tests/ and smoke() that executes oracle/ -- as the measured CPU baseline only.
+    Like the GPU arm, every instance runs its own closed-loop MPC loop (no lock-step between steps); instances are
+    handed to the threads dynamically (the analogue of Threads.@threads over the batch)."""
     from oracle.oracle import OracleProblem
 
     prob = copy.deepcopy(wl.prob)
     op = OracleProblem(prob)
-
-    class _S:
-        def shift_fill(self, primal=True, dual=True):
-            op.shift_fill(primal, dual)
-
     op.solve(wl.opts, nthreads=nthreads)  # initial solve (random_linear_problem.jl:113), not timed
-    zs = wl.noise_samples(steps + warmup)
-    k_save = wl.k.copy()
-    total, iters, status = 0.0, [], []
-    for st in range(steps + warmup):
-        wl.host_advance(prob, _S(), zs[st])
-        t0 = time.perf_counter()
-        r = op.solve(wl.opts, nthreads=nthreads)
-        dt = time.perf_counter() - t0
-        if st >= warmup:
-            total += dt
-            iters.append(r.iterations.mean())
-            status.append(np.mean(r.status == 1))
-    wl.k = k_save
-    return {"value": prob.B * steps / total, "seconds": total, "iters_mean": float(np.mean(iters)),
-            "success": float(np.mean(status))}
+    if wl.qstate is not None:  # quadruped: the contact schedule is rebuilt on the host every tick (lock-step)
+        class _S:
+            def shift_fill(self, primal=True, dual=True):
+                op.shift_fill(primal, dual)
+
+        total, iters, status = 0.0, [], []
+        for st in range(steps + warmup):
+            wl.host_advance(prob, _S(), None)
+            t0 = time.perf_counter()
+            r = op.solve(wl.opts, nthreads=nthreads)
+            if st >= warmup:
+                total += time.perf_counter() - t0
+                iters.append(r.iterations.mean())
+                status.append(np.mean(r.status == 1))
+        return {"value": prob.B * steps / total, "seconds": total, "iters_mean": float(np.mean(iters)),
+                "success": float(np.mean(status))}
+    k = wl.k.copy()
+    if warmup:
+        op.mpc_run(wl.opts, warmup, wl.noise_samples(warmup), wl.noise_model, wl.track, k, wl.shift, nthreads)
+        k = k + warmup
+    zs = wl.noise_samples(steps)
+    t0 = time.perf_counter()
+    r = op.mpc_run(wl.opts, steps, zs, wl.noise_model, wl.track, k, wl.shift, nthreads)
+    total = time.perf_counter() - t0
+    return {"value": prob.B * steps / total, "seconds": total, "iters_mean": float(r["iterations"].mean()),
+            "success": float(np.mean(r["status"] == 1))}
 
 
 # ----------------------------------------------------------------------------- main
@@ -287,7 +295,7 @@ def main():
     if wl.track is not None:
         sv.set_track(wl.track[0], wl.track[1], wl.k)
     sv.set_noise_model(*wl.noise_model)
-    sv.set_noise_bank(wl.noise_samples(W + K + 1))
+    sv.set_noise_bank(wl.noise_samples(max(W, 1) + 2 * K))
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -296,47 +304,59 @@ def main():
         torch.cuda.synchronize()
 
     qrng = mpc.rng_for(seed, 77)
+    fused = wl.qstate is None  # closed-loop run in one launch; quadruped rebuilds B_k on the host every tick
+    S_launch = K if fused else 1
 
-    def device_step():
-        if wl.qstate is not None:  # quadruped: the contact schedule moves, so B_k changes every tick (host-built)
-            quadruped.advance(prob, wl.qstate, qrng)
-            sv.upload()
-            sv.shift_fill(True, True)
-            sv.solve(fetch=True)
-        else:
-            sv.mpc_transition(None, shift=wl.shift)
-            sv.solve(fetch=False)
+    def q_tick(fetch):
+        quadruped.advance(prob, wl.qstate, qrng)
+        sv.upload()
+        sv.shift_fill(True, True)
+        sv.solve(fetch=fetch)
 
     # ---- initial solve + warm-up (untimed)
     sv.solve()
     init_ok = float(np.mean(sv.stats.status == 1))
-    for _ in range(W):
-        device_step()
-    sv.fetch()
+    if fused:
+        if W:
+            sv.mpc_run(W, shift=wl.shift)
+    else:
+        for _ in range(W):
+            q_tick(True)
     barrier()
-    # ---- timed region: K steps, CUDA events on the launching stream around every step
+    # ---- timed region: K steps, CUDA events on the launching stream around every launch
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    n_launch = K // S_launch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_launch)]
     kern_ms, flops, per_step = [], 0.0, []
     t_wall = time.perf_counter()
-    for st in range(K):
-        flush.zero_()  # L2 flush between timed iterations (256 MB write, outside the event pair)
-        if wl.qstate is not None:
+    for li in range(n_launch):
+        flush.zero_()  # L2 flush between timed launches (256 MB write, outside the event pair)
+        if fused:
+            ev[li][0].record(stream)
+            sv.mpc_run(S_launch, shift=wl.shift, fetch=False)
+            ev[li][1].record(stream)
+            rr = sv.run_results(S_launch)  # D2H after the event pair: needed for the flop model, not timed
+            kern_ms.append(rr["device_ms"])
+            flops += flops_model(prob, rr["iterations"], rr["iterations_outer"], rr["ls_trials"])
+            for st in range(S_launch):
+                per_step.append((float(rr["iterations"][st].mean()), float(rr["ls_trials"][st].mean()),
+                                 float(np.mean(rr["status"][st] == 1)), float(np.median(rr["t_us"][st])),
+                                 float(rr["t_us"][st].max())))
+            last_status, last_iters = rr["status"][-1], rr["iterations"][-1]
+        else:
             quadruped.advance(prob, wl.qstate, qrng)
             sv.upload()
-        ev[st][0].record(stream)
-        if wl.qstate is not None:
+            ev[li][0].record(stream)
             sv.shift_fill(True, True)
-        else:
-            sv.mpc_transition(None, shift=wl.shift)
-        sv.solve(fetch=False)
-        ev[st][1].record(stream)
-        stt = sv.fetch()  # D2H of the statistics after the event pair: needed for the flop model, not timed
-        kern_ms.append(stt.tsolve)
-        flops += flops_model(prob, stt.iterations, stt.iterations_outer, stt.ls_trials)
-        per_step.append((float(stt.iterations.mean()), float(stt.ls_trials.mean()), float(np.mean(stt.status == 1)),
-                         float(np.median(stt.t_instance_us)), float(stt.t_instance_us.max())))
+            sv.solve(fetch=False)
+            ev[li][1].record(stream)
+            stt = sv.fetch()
+            kern_ms.append(stt.tsolve)
+            flops += flops_model(prob, stt.iterations, stt.iterations_outer, stt.ls_trials)
+            per_step.append((float(stt.iterations.mean()), float(stt.ls_trials.mean()), float(np.mean(stt.status == 1)),
+                             float(np.median(stt.t_instance_us)), float(stt.t_instance_us.max())))
+            last_status, last_iters = stt.status, stt.iterations
     barrier()
     wall = time.perf_counter() - t_wall
     sampler.stop_flag.set()
@@ -344,36 +364,50 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_s = sharding.max_over_ranks(sum(step_ms) * 1e-3)
     kern_s = sum(kern_ms) * 1e-3
-    last = sv.stats
-    gathered = sharding.gather_stats({"iterations": last.iterations, "status": last.status, "c_max": last.c_max})
+    gathered = sharding.gather_stats({"iterations": last_iters, "status": last_status})
+
+    # ---- lock-step variant for the record: one transition + one solve launch per MPC step (every step waits
+    #      for the slowest instance of the batch)
+    lock = None
+    if fused:
+        evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for st in range(K):
+            flush.zero_()
+            evl[st][0].record(stream)
+            sv.mpc_transition(None, shift=wl.shift)
+            sv.solve(fetch=False)
+            evl[st][1].record(stream)
+        barrier()
+        t_lock = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evl) * 1e-3)
+        lock = {"value": B * world * K / t_lock, "unit": UNIT, "ms_per_step": 1e3 * t_lock / K,
+                "note": "one launch per MPC step: each step waits for the slowest instance"}
+        sv.fetch()
 
     # ---- e2e: same metric through the public API with host buffers
     e2e = None
     if not args.no_e2e:
-        zs = wl.noise_samples(K)
-        wl.k = wl.k + W + K  # the device-side loop advanced the track index this far
-        h2d = prob.x0.nbytes + (prob.Xref.nbytes + prob.Uref.nbytes if wl.track is not None else 0)
-        if wl.qstate is not None:
-            h2d += prob.model.A.nbytes + prob.model.B.nbytes + prob.model.d.nbytes
-        d2h = prob.X.nbytes + prob.U.nbytes + B * (4 * 4 + 4 * 8 + 8)
         barrier()
-        t_e2e = 0.0
-        for st in range(K):
-            if wl.qstate is not None:
-                quadruped.advance(prob, wl.qstate, qrng)
+        if fused:
+            zs = wl.noise_samples(K)
+            sv.lib.altro_host_register(S._p(zs), zs.nbytes)
+            h2d = zs.nbytes
+            d2h = K * B * (prob.n + prob.m) * 8 + K * B * (4 * 4 + 2 * 8 + 8) + prob.X.nbytes + prob.U.nbytes
+            t0 = time.perf_counter()
+            sv.set_noise_bank(zs)  # H2D of this run's inputs
+            sv.mpc_run(K, shift=wl.shift, fetch=True)  # run + D2H of closed-loop states, controls, statistics, X, U
+            t_e2e = time.perf_counter() - t0
+            sv.lib.altro_host_unregister(S._p(zs))
+            h2d, d2h = h2d / K, d2h / K
+        else:
+            h2d = prob.x0.nbytes + prob.model.A.nbytes + prob.model.B.nbytes + prob.model.d.nbytes
+            d2h = prob.X.nbytes + prob.U.nbytes + B * (4 * 4 + 4 * 8 + 8)
+            t_e2e = 0.0
+            for st in range(K):
+                quadruped.advance(prob, wl.qstate, qrng)  # host-side linearisation (the caller's work, not timed)
                 t0 = time.perf_counter()
-                sv.shift_fill(True, True)
-            else:
-                x0 = wl.apply_noise(prob.X[:, 1, :], zs[st])
-                prob.set_initial_state(x0)
-                if wl.track is not None:
-                    wl.k = wl.k + 1
-                    prob.update_trajectory(*mpc.window_reference(wl.track[0], wl.track[1], wl.k, prob.N))
-                t0 = time.perf_counter()
-                if wl.shift:
-                    sv.shift_fill(True, True)  # uploads the dirty host buffers first (pinned H2D), then shifts on device
-            sv.solve(fetch=True)  # H2D (if still dirty) + solve + D2H of X, U and statistics
-            t_e2e += time.perf_counter() - t0
+                sv.shift_fill(True, True)  # pinned H2D of x0 and A_k, B_k, d_k, then the shifts on the device
+                sv.solve(fetch=True)  # solve + D2H of X, U and statistics
+                t_e2e += time.perf_counter() - t0
         barrier()
         t_e2e = sharding.max_over_ranks(t_e2e)
         e2e = {"value": B * world * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -401,12 +435,17 @@ def main():
         "config": {"workload": wl.desc, "instances_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"instance-sharded x{world}, no collective on the solve path",
                    "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MB write)",
-                   "launch": info, "step": "device MPC transition + shift_fill + batched AL-iLQR solve"},
+                   "launch": info,
+                   "step": ("closed-loop MPC run: per instance K x {transition + shift_fill + AL-iLQR solve} in one "
+                            "launch, instances advance independently") if fused else
+                           "host-built dynamics upload + device shift_fill + batched AL-iLQR solve, one launch per step"},
         "p50_solve_us": float(np.median(ps[:, 3])), "max_solve_us": float(ps[:, 4].max()),
         "iters_mean": float(ps[:, 0].mean()), "ls_trials_mean": float(ps[:, 1].mean()),
         "success": float(ps[:, 2].mean()), "success_all_ranks_last_step": float(np.mean(gathered["status"] == 1)),
+        "iters_all_ranks_last_step": float(np.mean(gathered["iterations"])),
         "init_success": init_ok,
-        "gpu_launches": int((3 if wl.shift else 2) * K),
+        "gpu_launches": int(2 * n_launch if fused else 2 * K),
+        "steps_per_launch": S_launch,
         "clocks": sampler.summary(),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["dfma_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["dfma_tflops"], "traffic": None,
@@ -423,6 +462,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if lock:
+        line["lockstep"] = lock
     if world == 1 and not args.no_cpu_baseline:
         nt = host_threads()
         r = oracle_arm(Workload(args.workload, args.batch, seed, make_solver), args.cpu_steps, 1, nt)

@@ -154,6 +154,17 @@ int altro_get_x0(altro_handle_t h, double *x0);
  * whenever altro_mpc_transition is called with noise == NULL, so a closed-loop run has no host traffic. */
 int altro_set_noise_bank(altro_handle_t h, const double *noise, int steps);
 
+/* Closed-loop MPC run, entirely on the device: `steps` x {altro_mpc_transition; altro_solve} per instance inside
+ * ONE launch -- the body of run_MPC (random_linear_problem.jl:121-187) / run_Rocket_MPC (simple_rocket.jl:159-203)
+ * for every instance of the batch.  Instances advance independently (no lock-step between steps), noise comes
+ * from the noise bank, references from the track.  Starts from the current solution (an altro_solve must have
+ * run).  Per-step results: statistics [steps][B], closed-loop states x0_log[steps][B][n] (X_traj of the
+ * reference) and applied controls u0_log[steps][B][m], per-step device time per instance t_ns[steps][B]. */
+int altro_mpc_run(altro_handle_t h, int steps, int shift);
+int altro_get_run_results(altro_handle_t h, int steps, int *iterations, int *iterations_outer, int *status,
+                          int *ls_trials, double *cost, double *c_max, double *x0_log, double *u0_log,
+                          long long *t_ns);
+
 /* Pin / unpin a caller buffer so setters and getters DMA directly (cudaHostRegister). */
 int altro_host_register(void *ptr, size_t bytes);
 int altro_host_unregister(void *ptr);

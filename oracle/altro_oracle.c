@@ -818,58 +818,140 @@ static void solve_instance(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
 typedef struct {
     const orc_problem_t *pb;
     const orc_opts_t *o;
+    const orc_run_t *run; /* NULL: one plain solve per instance */
     int i1;
     atomic_int *next;
     double *X, *U, *lam;
     int *iters, *iters_outer, *status, *ls_trials;
     double *cost, *cost_al, *cmax, *pen_max;
+    double *x0_log, *u0_log;
 } job_t;
+
+/* Warm-started MPC transition of one instance (the kernel's Ctx::transition): x0 <- x_1 + noise, reference
+ * window advanced along the track, primal (controls) and dual shift_fill. Writes the instance's rows of the
+ * problem's x0 / xref / uref arrays, like the device does. */
+static void transition(const orc_problem_t *pb, const orc_run_t *run, ws_t *w, int inst, int st, double *lam)
+{
+    const int n = pb->n, m = pb->m, N = pb->N;
+    double *x0 = (double *)pb->x0 + (size_t)inst * n;
+    const double *xo = w->X + n;
+    const double *z = run->noise ? run->noise + ((size_t)st * pb->B + inst) * n : NULL;
+    double s0 = run->w1, s1 = run->w1;
+    if (z) {
+        if (run->noise_mode == 1) {
+            double mx = 0.0;
+            for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(xo[i]));
+            s0 = s1 = mx * run->w1;
+        } else if (run->noise_mode == 2) {
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < n / 2; ++i) a += xo[i] * xo[i];
+            for (int i = n / 2; i < n; ++i) b += xo[i] * xo[i];
+            s0 = sqrt(a) * run->w1;
+            s1 = sqrt(b) * run->w2;
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        double v = xo[i];
+        if (z) v += z[i] * ((run->noise_mode == 2 && i >= n / 2) ? s1 : s0);
+        x0[i] = v;
+    }
+    if (run->trackX) {
+        const int k0 = run->kidx[inst] + st + 1;
+        double *xr = (double *)pb->xref + (size_t)inst * N * n, *ur = (double *)pb->uref + (size_t)inst * (N - 1) * m;
+        for (int i = 0; i < N * n; ++i) {
+            int k = k0 + i / n;
+            if (k > run->Nt - 1) k = run->Nt - 1;
+            xr[i] = run->trackX[(size_t)k * n + i % n];
+        }
+        for (int i = 0; i < (N - 1) * m; ++i) {
+            int k = k0 + i / m;
+            if (k > run->Nt - 2) k = run->Nt - 2;
+            ur[i] = run->trackU[(size_t)k * m + i % m];
+        }
+    }
+    if (run->shift) {
+        if (N > 2) memmove(w->U, w->U + m, sizeof(double) * (size_t)(N - 2) * m);
+        double *l = lam;
+        for (int c = 0; c < pb->ncon; ++c) {
+            int nk = pb->con[c].k1 - pb->con[c].k0, p = pb->con[c].p;
+            if (nk > 1) memmove(l, l + p, sizeof(double) * (size_t)(nk - 1) * p);
+            l += (size_t)nk * p;
+        }
+    }
+}
 
 /* Worker: pulls instance ids from a shared counter (dynamic schedule, chunk 1). */
 static void *worker(void *arg)
 {
     job_t *j = (job_t *)arg;
     const orc_problem_t *pb = j->pb;
-    int n = pb->n, m = pb->m, N = pb->N;
+    int n = pb->n, m = pb->m, N = pb->N, B = pb->B;
     ws_t *w = ws_new(pb);
+    const int steps = j->run ? j->run->steps : 1;
     for (;;) {
         int i = atomic_fetch_add(j->next, 1);
         if (i >= j->i1) break;
         res_t r;
         double *l = j->lam + (size_t)i * w->P;
         memcpy(w->U, j->U + (size_t)i * (N - 1) * m, sizeof(double) * (size_t)(N - 1) * m);
-        solve_instance(pb, j->o, w, i, l, &r);
+        if (j->run) memcpy(w->X, j->X + (size_t)i * N * n, sizeof(double) * (size_t)N * n);
+        for (int st = 0; st < steps; ++st) {
+            if (j->run) {
+                transition(pb, j->run, w, i, st, l);
+                if (j->x0_log) memcpy(j->x0_log + ((size_t)st * B + i) * n, pb->x0 + (size_t)i * n, sizeof(double) * n);
+            }
+            solve_instance(pb, j->o, w, i, l, &r);
+            if (j->run && j->u0_log) memcpy(j->u0_log + ((size_t)st * B + i) * m, w->U, sizeof(double) * m);
+            const size_t at = (size_t)st * B + i;
+            if (j->iters) j->iters[at] = r.iters;
+            if (j->iters_outer) j->iters_outer[at] = r.outer;
+            if (j->status) j->status[at] = r.status;
+            if (j->ls_trials) j->ls_trials[at] = r.trials;
+            if (j->cost) j->cost[at] = objective_cost(pb, w, i, w->X, w->U);
+            if (j->cost_al) j->cost_al[at] = r.J;
+            if (j->cmax) j->cmax[at] = r.cmax;
+            if (j->pen_max) j->pen_max[at] = r.pen_max;
+        }
         memcpy(j->X + (size_t)i * N * n, w->X, sizeof(double) * (size_t)N * n);
         memcpy(j->U + (size_t)i * (N - 1) * m, w->U, sizeof(double) * (size_t)(N - 1) * m);
-        if (j->iters) j->iters[i] = r.iters;
-        if (j->iters_outer) j->iters_outer[i] = r.outer;
-        if (j->status) j->status[i] = r.status;
-        if (j->ls_trials) j->ls_trials[i] = r.trials;
-        if (j->cost) j->cost[i] = objective_cost(pb, w, i, w->X, w->U);
-        if (j->cost_al) j->cost_al[i] = r.J;
-        if (j->cmax) j->cmax[i] = r.cmax;
-        if (j->pen_max) j->pen_max[i] = r.pen_max;
     }
     ws_free(w);
     return NULL;
 }
 
-int orc_solve_batch(const orc_problem_t *pb, const orc_opts_t *o, int i0, int i1, int nthreads, double *X,
-                    double *U, double *lam, int *iters, int *iters_outer, int *status, int *ls_trials,
-                    double *cost, double *cost_al, double *cmax, double *pen_max)
+static int run_jobs(job_t *j, int i0, int nthreads)
 {
+    const orc_problem_t *pb = j->pb;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     for (int c = 0; c < pb->ncon; ++c)
         if (pb->con[c].w > ORC_MAX_W || pb->con[c].p > ORC_MAX_W) return -1;
     atomic_int next;
     atomic_init(&next, i0);
-    job_t j = {pb, o, i1, &next, X, U, lam, iters, iters_outer, status, ls_trials, cost, cost_al, cmax, pen_max};
+    j->next = &next;
     pthread_t th[256];
-    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, worker, &j);
-    worker(&j);
+    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, worker, j);
+    worker(j);
     for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
     return 0;
+}
+
+int orc_solve_batch(const orc_problem_t *pb, const orc_opts_t *o, int i0, int i1, int nthreads, double *X,
+                    double *U, double *lam, int *iters, int *iters_outer, int *status, int *ls_trials,
+                    double *cost, double *cost_al, double *cmax, double *pen_max)
+{
+    job_t j = {pb, o, NULL, i1, NULL, X, U, lam, iters, iters_outer, status, ls_trials, cost, cost_al, cmax, pen_max,
+               NULL, NULL};
+    return run_jobs(&j, i0, nthreads);
+}
+
+int orc_mpc_run(const orc_problem_t *pb, const orc_opts_t *o, const orc_run_t *run, int nthreads, double *X,
+                double *U, double *lam, int *iters, int *iters_outer, int *status, int *ls_trials, double *cost,
+                double *cmax, double *x0_log, double *u0_log)
+{
+    job_t j = {pb, o, run, pb->B, NULL, X, U, lam, iters, iters_outer, status, ls_trials, cost, NULL, cmax, NULL,
+               x0_log, u0_log};
+    return run_jobs(&j, 0, nthreads);
 }
 
 void orc_shift_fill(const orc_problem_t *pb, int primal, int dual, double *X, double *U, double *lam)

@@ -109,6 +109,22 @@ int orc_solve_batch(const orc_problem_t *pb, const orc_opts_t *o, int i0, int i1
                     int *iters, int *iters_outer, int *status, int *ls_trials,
                     double *cost, double *cost_al, double *cmax, double *pen_max);
 
+/* Closed-loop MPC run (the product's altro_mpc_run): per instance, `steps` x {transition; solve}, where the
+ * transition is x0 <- x_1 of the last solution + noise (modes as altro_set_noise_model), the reference window
+ * advanced along the track and the primal + dual shift_fill.  Instances run independently over the threads.
+ * Writes pb's x0 / xref / uref rows in place (the arrays must be writable).  Per-step outputs [steps][B]. */
+typedef struct {
+    int steps, shift, noise_mode, Nt;
+    double w1, w2;
+    const double *noise;           /* [steps][B][n] or NULL */
+    const double *trackX, *trackU; /* [Nt][n], [Nt-1][m] or NULL */
+    const int *kidx;               /* [B] window start before the run */
+} orc_run_t;
+
+int orc_mpc_run(const orc_problem_t *pb, const orc_opts_t *o, const orc_run_t *run, int nthreads, double *X,
+                double *U, double *lam, int *iters, int *iters_outer, int *status, int *ls_trials, double *cost,
+                double *cmax, double *x0_log, double *u0_log);
+
 /* Warm-start shifts (RD.shift_fill!, Altro.shift_fill!): z_k <- z_{k+1}, last kept. */
 void orc_shift_fill(const orc_problem_t *pb, int primal, int dual, double *X, double *U, double *lam);
 

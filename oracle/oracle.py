@@ -44,6 +44,12 @@ class _Opts(C.Structure):
             "soc_viol_proj")]
 
 
+class _Run(C.Structure):
+    _fields_ = [("steps", C.c_int), ("shift", C.c_int), ("noise_mode", C.c_int), ("Nt", C.c_int),
+                ("w1", C.c_double), ("w2", C.c_double), ("noise", C.c_void_p), ("trackX", C.c_void_p),
+                ("trackU", C.c_void_p), ("kidx", C.c_void_p)]
+
+
 def build(force: bool = False) -> str:
     src = [os.path.join(_HERE, f) for f in ("altro_oracle.c", "altro_oracle.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
@@ -134,6 +140,37 @@ class OracleProblem:
         if rc != 0:
             raise RuntimeError(f"orc_solve_batch failed: {rc}")
         return OracleResult(pr.X.copy(), pr.U.copy(), self.lam.copy(), it, ito, st, ls, cost, cal, cmax, pmax)
+
+    def mpc_run(self, opts, steps, noise=None, noise_model=(0, 1.0, 1.0), track=None, kidx=None, shift=True,
+                nthreads: int = 1) -> dict:
+        """Closed-loop run mirroring the product's altro_mpc_run; per-step results [steps][B]."""
+        pr, B = self.prob, self.prob.B
+        run = _Run()
+        run.steps, run.shift, run.noise_mode = steps, int(shift), int(noise_model[0])
+        run.w1, run.w2 = float(noise_model[1]), float(noise_model[2])
+        keep = []
+        if noise is not None:
+            nz = np.ascontiguousarray(noise, dtype=np.float64)
+            assert nz.shape == (steps, B, pr.n)
+            keep.append(nz)
+            run.noise = _ptr(nz)
+        if track is not None:
+            Xt = np.ascontiguousarray(track[0], dtype=np.float64)
+            Ut = np.ascontiguousarray(track[1], dtype=np.float64)
+            ki = np.ascontiguousarray(kidx, dtype=np.int32)
+            keep += [Xt, Ut, ki]
+            run.trackX, run.trackU, run.kidx, run.Nt = _ptr(Xt), _ptr(Ut), _ptr(ki), Xt.shape[0]
+        it, ito, st, ls = (np.zeros((steps, B), np.int32) for _ in range(4))
+        cost, cmax = np.zeros((steps, B)), np.zeros((steps, B))
+        x0l, u0l = np.zeros((steps, B, pr.n)), np.zeros((steps, B, pr.m))
+        o = _opts_struct(opts)
+        rc = lib().orc_mpc_run(C.byref(self.c), C.byref(o), C.byref(run), nthreads, _ptr(pr.X), _ptr(pr.U),
+                               _ptr(self.lam), _ptr(it), _ptr(ito), _ptr(st), _ptr(ls), _ptr(cost), _ptr(cmax),
+                               _ptr(x0l), _ptr(u0l))
+        if rc != 0:
+            raise RuntimeError(f"orc_mpc_run failed: {rc}")
+        return {"iterations": it, "iterations_outer": ito, "status": st, "ls_trials": ls, "cost": cost, "c_max": cmax,
+                "x0": x0l, "u0": u0l}
 
     def set_trace(self, rows: int):
         self.trace = np.zeros((self.prob.B, rows, 10)) if rows else None

@@ -266,3 +266,44 @@ def test_oversized_problem_is_an_error_not_a_fallback():
 
     with pytest.raises(AltroError, match="shared memory"):
         gpu_solver(prob, SolverOptions()).solve()
+
+
+# ------------------------------------------------------------------ closed-loop run in one launch
+
+@pytest.mark.parametrize("family", ["rocket", "random_linear"])
+def test_closed_loop_run_matches_oracle_and_stepwise_path(family):
+    """altro_mpc_run (steps x {transition; solve} per instance in ONE launch) against the oracle's orc_mpc_run and
+    against the same steps issued one launch at a time."""
+    B, steps = 96, 5
+    if family == "rocket":
+        cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+        Xt, Ut = cold["X"], cold["U"]
+        prob, opts, _, _ = cases.case_rocket_mpc(Xt, Ut, batch=B)
+        ks = mpc.rng_for(11, 0).integers(0, Xt.shape[0] - 21 - 110, size=B)
+        model = (2, 1e-3, 1e-2)
+    else:
+        prob, Xt, Ut, ks = random_linear.mpc_problem(12, 6, 21, batch=B, seed=12)
+        opts, model = random_linear.mpc_options(), (1, 0.01, 0.0)
+    noise = mpc.rng_for(3, 3).standard_normal((steps, B, prob.n))
+    pg, ps = copy.deepcopy(prob), copy.deepcopy(prob)
+    o = OracleSolver(prob, opts, nthreads=8).solve()
+    g, s = gpu_solver(pg, opts).solve(), gpu_solver(ps, opts).solve()
+    for sv in (g, s):
+        sv.set_track(Xt, Ut, ks)
+        sv.set_noise_model(*model)
+        sv.set_noise_bank(noise)
+    rg = g.mpc_run(steps)
+    ro = o.op.mpc_run(opts, steps, noise, model, (Xt, Ut), ks, True, nthreads=8)
+    for k in ro:
+        assert np.array_equal(rg[k], ro[k]), k
+    assert np.array_equal(pg.X, prob.X) and np.array_equal(pg.U, prob.U) and np.array_equal(g.get_duals(), o.op.lam)
+    assert np.array_equal(g.get_x0(), prob.x0)
+    assert np.mean(rg["status"] == 1) > 0.99
+    for st in range(steps):  # the same run, one transition + one solve launch per step
+        s.mpc_transition(None, shift=True)
+        s.solve()
+        assert np.array_equal(s.stats.iterations, rg["iterations"][st]), st
+        assert np.array_equal(ps.X[:, 0], rg["x0"][st]) and np.array_equal(ps.U[:, 0], rg["u0"][st])
+    assert np.array_equal(ps.X, pg.X) and np.array_equal(ps.U, pg.U)
+    # and the run can be continued: two runs of 2 + 3 steps equal one of 5
+    pc = copy.deepcopy(prob)  # prob was advanced by the oracle run; rebuild the starting point instead
