@@ -54,12 +54,14 @@ struct altro_handle_s {
     long long *t_ns = nullptr;
     int stat_cap = 1;  // statistics arrays hold stat_cap x B entries (one slot per step of a closed-loop run)
     double *x0_log = nullptr, *u0_log = nullptr;
+    long long *phase = nullptr;
     double *trace = nullptr;
     int trace_rows = 0;
     // constraints
     std::vector<HostCon> cons;
     ConDesc *con_dev = nullptr;
-    int P = 0, EX = 0;
+    int *itab_dev = nullptr;
+    int P = 0, EX = 0, ITAB = 0;
     bool finalized = false, have_dyn = false, have_cost = false, have_ref = false, have_x0 = false;
     // MPC track
     double *trackX = nullptr, *trackU = nullptr, *noise = nullptr, *noise_bank = nullptr;
@@ -255,7 +257,9 @@ int finalize(altro_handle_t h)
     const int n = h->n, m = h->m, N = h->N, B = h->B;
     // dual / expansion offsets, device descriptors
     std::vector<ConDesc> cd(std::max<size_t>(h->cons.size(), 1));
-    int P = 0, EX = 0;
+    int P = 0, EX = 0, TG = 0;
+    const int NT = n + n * n + m + m * m;
+    std::vector<std::vector<int>> srcs(NT);
     for (size_t i = 0; i < h->cons.size(); ++i) {
         HostCon &c = h->cons[i];
         ConDesc &dsc = cd[i];
@@ -265,6 +269,19 @@ int finalize(altro_handle_t h)
         dsc.dual_off = P;
         dsc.ex_off = EX;
         dsc.ex_stride = c.rowsparse ? 2 * c.w : c.w + c.w * c.w;
+        dsc.tgt_off = TG;
+        TG += dsc.ex_stride;
+        // gather sources: (block, offset inside the block's per-knot expansion) for every target it touches
+        const int ld = c.side == ALTRO_STATE ? n : m;
+        const int ovec = c.side == ALTRO_STATE ? 0 : n + n * n, omat = ovec + ld;
+        for (int e = 0; e < c.w; ++e) srcs[ovec + c.inds[e]].push_back(((int)i << 16) | e);
+        if (c.rowsparse) {
+            for (int e = 0; e < c.w; ++e) srcs[omat + c.inds[e] * ld + c.inds[e]].push_back(((int)i << 16) | (c.w + e));
+        } else {
+            for (int a = 0; a < c.w; ++a)
+                for (int b = 0; b < c.w; ++b)
+                    srcs[omat + c.inds[a] * ld + c.inds[b]].push_back(((int)i << 16) | (c.w + a * c.w + b));
+        }
         dsc.G = c.G_dev; dsc.h = c.h_dev; dsc.rs_col = c.rs_col_dev; dsc.rs_coef = c.rs_coef_dev;
         for (int j = 0; j < c.w; ++j) dsc.inds[j] = c.inds[j];
         P += (c.k1 - c.k0) * c.p;
@@ -272,6 +289,14 @@ int finalize(altro_handle_t h)
     }
     h->P = P;
     h->EX = EX;
+    {  // CSR gather table: gptr[NT+1] then gsrc[]; per target the sources stay in ascending block order
+        std::vector<int> itab(NT + 1, 0);
+        for (int t = 0; t < NT; ++t) itab[t + 1] = itab[t] + (int)srcs[t].size();
+        for (int t = 0; t < NT; ++t) itab.insert(itab.end(), srcs[t].begin(), srcs[t].end());
+        h->ITAB = (int)itab.size();
+        CK(h, dalloc(&h->itab_dev, itab.size()));
+        CK(h, cudaMemcpy(h->itab_dev, itab.data(), itab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     CK(h, dalloc(&h->con_dev, cd.size()));
     CK(h, cudaMemcpy(h->con_dev, cd.data(), cd.size() * sizeof(ConDesc), cudaMemcpyHostToDevice));
     CK(h, dalloc(&h->lam, (size_t)B * P));
@@ -288,14 +313,14 @@ int finalize(altro_handle_t h)
     h->threads = T;
     h->dyn_in_smem = (!h->dyn_per_knot && !h->dyn_per_instance) ? 1 : 0;
     h->ref_in_smem = 1;
-    size_t smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 1, T);
+    size_t smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 1, T, h->ITAB);
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {  // long horizons: keep the reference in global memory
         h->ref_in_smem = 0;
-        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 0, T);
+        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 0, T, h->ITAB);
     }
     if (smem > (size_t)prop.sharedMemPerBlockOptin && h->dyn_in_smem) {
         h->dyn_in_smem = 0;
-        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, 0, 0, T);
+        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, 0, 0, T, h->ITAB);
     }
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {
         char buf[256];
@@ -423,7 +448,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->trace, h->con_dev, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -525,8 +550,11 @@ int altro_add_constraint(altro_handle_t h, int sense, int side, int k0, int k1, 
     if (k0 < 0 || k1 > kmax || k1 <= k0) return fail(h, ALTRO_ERR_INVALID, "bad knot range (control blocks end at N-1)");
     if (w > MAX_W) return fail(h, ALTRO_ERR_UNSUPPORTED, "constraint index set wider than 32");
     const int lim = side == ALTRO_CONTROL ? h->m : h->n;
-    for (int j = 0; j < w; ++j)
+    for (int j = 0; j < w; ++j) {
         if (inds[j] < 0 || inds[j] >= lim) return fail(h, ALTRO_ERR_INVALID, "constraint index out of range");
+        for (int q = 0; q < j; ++q)
+            if (inds[q] == inds[j]) return fail(h, ALTRO_ERR_INVALID, "duplicate index in a constraint block");
+    }
     if (sense == ALTRO_SECOND_ORDER_CONE && p < 2) return fail(h, ALTRO_ERR_INVALID, "a cone block needs >= 2 rows");
     HostCon c;
     c.sense = sense; c.side = side; c.k0 = k0; c.k1 = k1; c.p = p; c.w = w;
@@ -549,7 +577,8 @@ int altro_add_constraint(altro_handle_t h, int sense, int side, int k0, int k1, 
         }
         if (rs) { c.rowsparse = 1; c.rs_col = col; c.rs_coef = coef; }
     }
-    if (!c.rowsparse && p > PMAX) return fail(h, ALTRO_ERR_UNSUPPORTED, "dense constraint block with more than 16 rows");
+    if (!c.rowsparse && (p > PMAX || w > DENSE_W))
+        return fail(h, ALTRO_ERR_UNSUPPORTED, "dense constraint block larger than 8 rows x 8 indices");
     CK(h, dalloc(&c.G_dev, c.g_count));
     CK(h, dalloc(&c.h_dev, c.h_count));
     CK(h, cudaMemcpy(c.G_dev, G, c.g_count * sizeof(double), cudaMemcpyHostToDevice));
@@ -670,7 +699,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
 {
     Params P;
     memset(&P, 0, sizeof(P));
-    P.n = h->n; P.m = h->m; P.N = h->N; P.B = h->B; P.P = h->P; P.ncon = (int)h->cons.size(); P.EX = h->EX;
+    P.n = h->n; P.m = h->m; P.N = h->N; P.B = h->B; P.P = h->P; P.ncon = (int)h->cons.size(); P.EX = h->EX; P.ITAB = h->ITAB;
     P.inst_offset = 0;
     P.dt = h->dt;
     P.dyn_per_knot = h->dyn_per_knot; P.dyn_per_instance = h->dyn_per_instance; P.dyn_in_smem = h->dyn_in_smem; P.ref_in_smem = h->ref_in_smem;
@@ -684,6 +713,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     P.trace = h->trace;
     P.trace_rows = h->trace_rows;
     P.con = h->con_dev;
+    P.itab = h->itab_dev;
     P.o = h->opts;
     P.steps = steps; P.shift = shift; P.noise_mode = h->noise_mode; P.Nt = h->Nt;
     P.noise_w1 = h->noise_w1; P.noise_w2 = h->noise_w2;
@@ -697,6 +727,8 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
         P.trackX = h->trackX; P.trackU = h->trackU; P.kidx = h->kidx;
         P.x0_log = h->x0_log; P.u0_log = h->u0_log;
     }
+    P.phase = h->phase;
+    P.phase_detail = getenv("ALTRO_B200_PHASE_DETAIL") ? 1 : 0;
     void *args[] = {&P};
     if (h->trace)
         CK(h, cudaMemsetAsync(h->trace, 0, (size_t)h->B * h->trace_rows * TRACE_COLS * sizeof(double), h->stream));
@@ -818,6 +850,17 @@ int altro_get_trace(altro_handle_t h, double *out)
     int rc = download(h, out, h->trace, (size_t)h->B * h->trace_rows * TRACE_COLS * sizeof(double));
     if (rc) return rc;
     CK(h, cudaStreamSynchronize(h->stream));
+    return ALTRO_OK;
+}
+
+int altro_get_phase_cycles(altro_handle_t h, int enable, long long *out)
+{
+    REQ(h);
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (out && h->phase) CK(h, cudaMemcpy(out, h->phase, (size_t)h->B * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (enable && !h->phase) CK(h, dalloc(&h->phase, (size_t)h->B * 8));
+    if (enable) CK(h, cudaMemset(h->phase, 0, (size_t)h->B * 8 * sizeof(long long)));
+    if (!enable && h->phase) { cudaFree(h->phase); h->phase = nullptr; }
     return ALTRO_OK;
 }
 

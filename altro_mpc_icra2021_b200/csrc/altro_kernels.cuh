@@ -21,7 +21,8 @@ namespace altro {
 
 constexpr int MAX_CON = 16;  // constraint blocks per problem
 constexpr int MAX_W = 32;    // index-set width of one block
-constexpr int PMAX = 16;     // rows of a dense block (row-sparse blocks are unlimited)
+constexpr int PMAX = 8;      // rows of a dense block (row-sparse blocks are unlimited)
+constexpr int DENSE_W = 8;   // index-set width of a dense block
 constexpr int TRACE_COLS = 10;  // outer, iter, J, dJ, grad, rho, dV1, dV2, ls trials so far, c_max (NaN inside an outer)
 
 // One affine conic block c = G z[inds] + h (device view).
@@ -32,6 +33,7 @@ struct ConDesc {
     int dual_off;   // offset of the block in the per-instance dual vector
     int ex_off;     // offset of the block in the per-instance expansion scratch
     int ex_stride;  // per-knot stride there: w + w*w (dense) or 2*w (row-sparse)
+    int tgt_off;    // offset of the block's scatter targets in the shared int table (ex_stride entries)
     const double *G, *h;
     const int *rs_col;
     const double *rs_coef;
@@ -39,7 +41,7 @@ struct ConDesc {
 };
 
 struct Params {
-    int n, m, N, B, P, ncon, EX;
+    int n, m, N, B, P, ncon, EX, ITAB;
     int inst_offset;
     double dt;
     int dyn_per_knot, dyn_per_instance, dyn_in_smem, ref_in_smem;
@@ -58,7 +60,10 @@ struct Params {
     const double *trackX, *trackU;  // reference track [Nt][n], [Nt-1][m], or nullptr
     const int *kidx;                // per-instance track index of the current window start
     double *x0_log, *u0_log;        // [steps][B][n], [steps][B][m]: closed-loop state and applied control
+    int phase_detail;               // 1: phase[] holds the backward-pass sub-phase split instead
+    long long *phase;               // optional [B][8] cycle counters per phase (profiling aid), or nullptr
     const ConDesc *con;
+    const int *itab;  // gather lists built by the host: gptr[NT+1] then gsrc[]
     altro_opts_t o;
 };
 
@@ -68,24 +73,26 @@ __host__ __device__ inline size_t smem_doubles(int n, int m, int N, int P, int n
 {
     size_t s = 0;
     s += (size_t)2 * n + m;                                   // Q, Qf, R
-    s += dyn_in_smem ? (size_t)n * n + (size_t)n * m + n : 0;  // shared LTI dynamics
+    s += (size_t)n * n + (size_t)n * m + n;                   // A, B, d: shared LTI dynamics, or the LTV knot being processed
+    (void)dyn_in_smem;
     s += (size_t)2 * ((size_t)N * n + (size_t)(N - 1) * m);   // X,U,Xb,Ub
     s += ref_in_smem ? (size_t)N * n + (size_t)(N - 1) * m : 0;  // xref, uref
     s += (size_t)(N - 1) * m * n + (size_t)(N - 1) * m;       // K, d
     s += (size_t)P + MAX_CON;                                 // duals, penalties
     s += (size_t)EX;                                          // expansion scratch
     s += (size_t)3 * n * n + (size_t)n * m + (size_t)2 * m * n + (size_t)2 * m * m;  // S,SA,Qxx,SB,Qux,T1,Quu,L
-    s += (size_t)3 * n + (size_t)4 * m;                       // s,Qx,(spare) ; Qu,t1,ldiag,(spare)
+    s += (size_t)3 * n + (size_t)4 * m;                       // s,Qx,(spare) ; Qu,t1,ldiag,linv
     s += (size_t)T / 32 + 8;                                  // reduction scratch + broadcast slots
     s += (size_t)N * (1 + ncon);                              // per-(knot, piece) cost items
     return s;
 }
 
 __host__ __device__ inline size_t smem_bytes(int n, int m, int N, int P, int ncon, int EX, int dyn_in_smem,
-                                              int ref_in_smem, int T)
+                                              int ref_in_smem, int T, int ITAB)
 {
     size_t b = smem_doubles(n, m, N, P, ncon, EX, dyn_in_smem, ref_in_smem, T) * sizeof(double);
     b += (size_t)(ncon > 0 ? ncon : 1) * sizeof(ConDesc);
+    b += (size_t)ITAB * sizeof(int);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -142,7 +149,11 @@ struct Ctx {
     // shared memory
     double *Qd, *Qfd, *Rd, *sA, *sB, *sd;
     double *X, *U, *Xb, *Ub, *xr, *ur, *K, *dv, *lam, *mu, *ex;
-    double *S, *SA, *Qxx, *SB, *Qux, *T1, *Quu, *L, *s, *Qx, *Qu, *t1, *ldiag, *red, *bc, *itm;
+    double *S, *SA, *Qxx, *SB, *Qux, *T1, *Quu, *L, *s, *Qx, *Qu, *t1, *ldiag, *linv, *red, *bc, *itm;
+    int *gptr, *gsrc;  // gather lists: for every entry of [Qx | Qxx | Qu | Quu] the (block << 16 | offset) sources
+    int NT;
+    long long ph_exp = 0, ph_roll = 0, ph_cost = 0;  // profiling aid (P.phase)
+    long long bpc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     ConDesc *cd;
     size_t dyn_base;
     int dyn_k;
@@ -159,8 +170,7 @@ struct Ctx {
         Qd = q; q += n;
         Qfd = q; q += n;
         Rd = q; q += m;
-        if (P.dyn_in_smem) { sA = q; q += n * n; sB = q; q += n * m; sd = q; q += n; }
-        else sA = sB = sd = nullptr;
+        sA = q; q += n * n; sB = q; q += n * m; sd = q; q += n;
         X = q; q += N * n;
         U = q; q += (N - 1) * m;
         Xb = q; q += N * n;
@@ -189,11 +199,14 @@ struct Ctx {
         Qu = q; q += m;
         t1 = q; q += m;
         ldiag = q; q += m;
-        q += m;
+        linv = q; q += m;
         red = q; q += T / 32;
         bc = q; q += 8;
         itm = q; q += N * (1 + ncon);
         cd = reinterpret_cast<ConDesc *>(q);
+        NT = n + n * n + m + m * m;
+        gptr = reinterpret_cast<int *>(cd + (ncon > 0 ? ncon : 1));
+        gsrc = gptr + NT + 1;
         dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_per_knot ? (size_t)(N - 1) : 1) : 0;
         dyn_k = P.dyn_per_knot ? 1 : 0;
     }
@@ -221,7 +234,7 @@ struct Ctx {
     {
         for (int i = tid; i < n; i += T) { Qd[i] = P.Q[i]; Qfd[i] = P.Qf[i]; }
         for (int i = tid; i < m; i += T) Rd[i] = P.R[i];
-        if (P.dyn_in_smem) {
+        if (P.dyn_in_smem) {  // shared LTI model
             for (int i = tid; i < n * n; i += T) sA[i] = P.A[i];
             for (int i = tid; i < n * m; i += T) sB[i] = P.Bm[i];
             for (int i = tid; i < n; i += T) sd[i] = P.d[i];
@@ -248,6 +261,7 @@ struct Ctx {
         const int *src = reinterpret_cast<const int *>(P.con);
         int *dst = reinterpret_cast<int *>(cd);
         for (int i = tid; i < words; i += T) dst[i] = src[i];
+        for (int i = tid; i < P.ITAB; i += T) gptr[i] = P.itab[i];
         gsync<T>();
     }
 
@@ -337,10 +351,9 @@ struct Ctx {
     __device__ double al_cost(const double *Xc, const double *Uc) const
     {
         const int items = N * (1 + ncon);
-        for (int it = tid; it < items; it += T) {
-            int k = it % N, j = it / N;
-            itm[it] = (j == 0) ? stage_cost(k, Xc, Uc) : con_cost(j - 1, k, Xc, Uc);
-        }
+        for (int k = tid; k < N; k += T) itm[k] = stage_cost(k, Xc, Uc);
+        for (int j = 0; j < ncon; ++j)
+            for (int k = tid; k < N; k += T) itm[(j + 1) * N + k] = con_cost(j, k, Xc, Uc);
         gsync<T>();
         return csum<T>(itm, items, bc);
     }
@@ -475,7 +488,7 @@ struct Ctx {
                         }
                 } else {
                     // lb = lam - mu c ; Pi(lb) ; g = -G' Pi(lb) ; H = mu G' dPi(lb) G  (structured)
-                    double lb[PMAX], q[MAX_W];
+                    double lb[PMAX], q[DENSE_W];
                     double a2 = 0.0;
                     for (int r = 0; r < p; ++r) {
                         lb[r] = l[r] - mu_c * row_value(c, G, h, z, r);
@@ -524,31 +537,16 @@ struct Ctx {
         gsync<T>();
     }
 
-    // Add the expansions of every block of `side` active at knot k into (vec, mat[ld x ld]).
-    __device__ void scatter_expansion(int k, int side, double *vec, double *mat, int ld)
+    // Sum of the AL expansion entries that land on target t of [Qx | Qxx | Qu | Quu] at knot k, added to `base`
+    // in ascending block order (the order the oracle's scatter uses).
+    __device__ __forceinline__ double gather(int t, int k, double base) const
     {
-        for (int ci = 0; ci < ncon; ++ci) {
-            const ConDesc &c = cd[ci];
-            if (c.side != side || k < c.k0 || k >= c.k1) continue;  // uniform across the CTA
-            const double *g = ex + c.ex_off + (k - c.k0) * c.ex_stride;
-            const int w = c.w;
-            if (c.rowsparse) {
-                for (int e = tid; e < w; e += T) {
-                    int zi = c.inds[e];
-                    vec[zi] += g[e];
-                    mat[zi * ld + zi] += g[w + e];
-                }
-            } else {
-                for (int e = tid; e < w + w * w; e += T) {
-                    if (e < w) vec[c.inds[e]] += g[e];
-                    else {
-                        int i = (e - w) / w, j = (e - w) - i * w;
-                        mat[c.inds[i] * ld + c.inds[j]] += g[e];
-                    }
-                }
-            }
-            gsync<T>();
+        for (int q = gptr[t]; q < gptr[t + 1]; ++q) {
+            const int src = gsrc[q];
+            const ConDesc &c = cd[src >> 16];
+            if (k >= c.k0 && k < c.k1) base += ex[c.ex_off + (k - c.k0) * c.ex_stride + (src & 0xffff)];
         }
+        return base;
     }
 
     // ---------------------------------------------------------------- backward pass (A.7)
@@ -564,146 +562,295 @@ struct Ctx {
         rho = (r > P.o.bp_reg_min) ? r : 0.0;
     }
 
+    // ---- FP64 tensor-core tiles.  One warp owns one 8x8 output tile:  C += sum_k A(i,k) B(k,j), k ascending.
+    // mma.sync.m8n8k4.f64 accumulates exactly like the scalar chain  acc = fma(a_k, b_k, acc), k = 0..3, starting
+    // from C (probed on B200: scripts/probes/dmma_order.cu, 1.28 M elements bit-identical), so the CPU oracle's
+    // plain fma loops reproduce every tile bit for bit.  Operands outside the matrix are fetched as 0.0.
+    // Fragment layout: lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4)] and C[l/4][2(l%4)+1].
+    template <class FA, class FB>
+    __device__ __forceinline__ void mma_chain(double &c0, double &c1, int K, FA a_at, FB b_at) const
+    {
+        const int lane = tid & 31, r = lane >> 2, q = lane & 3;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            const double a = a_at(r, k0 + q), b = b_at(k0 + q, r);
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0), "+d"(c1)
+                         : "d"(a), "d"(b));
+        }
+    }
+
     // Returns false if Quu could not be made positive definite.
     __device__ bool backward_pass(double &rho, double &drho, double &dV1, double &dV2)
     {
-        expand_constraints();
+        {
+            const long long ce = clock64();
+            expand_constraints();
+            ph_exp += clock64() - ce;
+        }
+        constexpr int NW = T / 32;
+        const int warp = tid >> 5, lane = tid & 31;
+        const int fr = lane >> 2, fc = 2 * (lane & 3);  // this lane's row / first column inside a tile
+        const int tn = (n + 7) >> 3, tm = (m + 7) >> 3, tn1 = (n + 8) >> 3, tm1 = (m + 8) >> 3;
+        const int oQxx = n, oQu = n + n * n, oQuu = n + n * n + m;
+        const double *A = sA, *Bm = sB;  // always shared memory here (LTV knots are staged below)
         for (;;) {
             bool restart = false;
             double a1 = 0.0, a2 = 0.0;  // dV accumulators, kept by thread T-1
             // terminal cost-to-go: S = Qf + state-side AL Hessian, s = Qf (x - xref) + AL gradient
-            for (int e = tid; e < n * n; e += T) {
-                int i = e / n, j = e - i * n;
-                S[e] = (i == j) ? Qfd[i] : 0.0;
+            for (int t = tid; t < oQu; t += T) {
+                if (t < n) s[t] = gather(t, N - 1, Qfd[t] * (X[(N - 1) * n + t] - xr[(N - 1) * n + t]));
+                else {
+                    const int e = t - n, i = e / n, j = e - i * n;
+                    S[e] = gather(t, N - 1, (i == j) ? Qfd[i] : 0.0);
+                }
             }
-            for (int i = tid; i < n; i += T) s[i] = Qfd[i] * (X[(N - 1) * n + i] - xr[(N - 1) * n + i]);
             gsync<T>();
-            scatter_expansion(N - 1, ALTRO_STATE, s, S, n);
             for (int k = N - 2; k >= 0; --k) {
-                const double *A = Ak(k), *Bm = Bk(k);
-                // P1: SA = S A, SB = S B ; cost expansion into Qxx,Quu,Qx,Qu
-                for (int e = tid; e < n * (n + m); e += T) {
-                    int i = e / (n + m), j = e - i * (n + m);
-                    const double *Si = S + i * n;
-                    double acc = 0.0;
-                    if (j < n) {
-                        for (int l = 0; l < n; ++l) acc = fma(Si[l], A[l * n + j], acc);
-                        SA[i * n + j] = acc;
+                long long tq = clock64(), tq2;
+#define ALTRO_TICK(slot) do { tq2 = clock64(); bpc[slot] += tq2 - tq; tq = tq2; } while (0)
+                if (!P.dyn_in_smem) {  // LTV: stage A_k, B_k into shared memory (coalesced), d_k is not needed here
+                    const double *gA = P.A + (dyn_base + (size_t)dyn_k * k) * n * n;
+                    const double *gB = P.Bm + (dyn_base + (size_t)dyn_k * k) * n * m;
+                    for (int i = tid; i < n * n; i += T) sA[i] = gA[i];
+                    for (int i = tid; i < n * m; i += T) sB[i] = gB[i];
+                    gsync<T>();
+                }
+                // P1: SA = S A, SB = S B (tensor tiles); cost + AL expansion gathered into Qx, Qxx, Qu, Quu
+                for (int t = warp; t < tn * (tn + tm); t += NW) {
+                    const int r0 = (t / (tn + tm)) << 3, ct = t % (tn + tm);
+                    const int i = r0 + fr;
+                    double d0 = 0.0, d1 = 0.0;
+                    if (ct < tn) {
+                        const int c0 = ct << 3, j = c0 + fc;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
+                                  [&](int l, int jj) { jj += c0; return (l < n && jj < n) ? A[l * n + jj] : 0.0; });
+                        if (i < n) {
+                            if (j < n) SA[i * n + j] = d0;
+                            if (j + 1 < n) SA[i * n + j + 1] = d1;
+                        }
                     } else {
-                        j -= n;
-                        for (int l = 0; l < n; ++l) acc = fma(Si[l], Bm[l * m + j], acc);
-                        SB[i * m + j] = acc;
+                        const int c0 = (ct - tn) << 3, j = c0 + fc;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
+                                  [&](int l, int jj) { jj += c0; return (l < n && jj < m) ? Bm[l * m + jj] : 0.0; });
+                        if (i < n) {
+                            if (j < m) SB[i * m + j] = d0;
+                            if (j + 1 < m) SB[i * m + j + 1] = d1;
+                        }
                     }
                 }
-                for (int e = tid; e < n * n; e += T) {
-                    int i = e / n, j = e - i * n;
-                    Qxx[e] = (i == j) ? P.dt * Qd[i] : 0.0;
-                }
-                for (int e = tid; e < m * m; e += T) {
-                    int i = e / m, j = e - i * m;
-                    Quu[e] = (i == j) ? P.dt * Rd[i] : 0.0;
-                }
-                for (int i = tid; i < n; i += T) Qx[i] = P.dt * Qd[i] * (X[k * n + i] - xr[k * n + i]);
-                for (int i = tid; i < m; i += T) Qu[i] = P.dt * Rd[i] * (U[k * m + i] - ur[k * m + i]);
-                gsync<T>();
-                scatter_expansion(k, ALTRO_STATE, Qx, Qxx, n);
-                scatter_expansion(k, ALTRO_CONTROL, Qu, Quu, m);
-                // P2: Qxx += A'SA, Qux = B'SA, Quu += B'SB, Qx += A's, Qu += B's
-                const int o1 = n * n, o2 = o1 + m * n, o3 = o2 + m * m, o4 = o3 + n, o5 = o4 + m;
-                for (int e = tid; e < o5; e += T) {
-                    double acc = 0.0;
-                    if (e < o1) {
-                        int i = e / n, j = e - i * n;
-                        for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], SA[l * n + j], acc);
-                        Qxx[e] += acc;
-                    } else if (e < o2) {
-                        int f = e - o1, i = f / n, j = f - i * n;
-                        for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], SA[l * n + j], acc);
-                        Qux[f] = acc;
-                    } else if (e < o3) {
-                        int f = e - o2, i = f / m, j = f - i * m;
-                        for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], SB[l * m + j], acc);
-                        Quu[f] += acc;
-                    } else if (e < o4) {
-                        int i = e - o3;
-                        for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], s[l], acc);
-                        Qx[i] += acc;
+                for (int t = tid; t < NT; t += T) {
+                    if (t < oQxx) Qx[t] = gather(t, k, P.dt * Qd[t] * (X[k * n + t] - xr[k * n + t]));
+                    else if (t < oQu) {
+                        const int e = t - oQxx, i = e / n, j = e - i * n;
+                        Qxx[e] = gather(t, k, (i == j) ? P.dt * Qd[i] : 0.0);
+                    } else if (t < oQuu) {
+                        const int i = t - oQu;
+                        Qu[i] = gather(t, k, P.dt * Rd[i] * (U[k * m + i] - ur[k * m + i]));
                     } else {
-                        int i = e - o4;
-                        for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], s[l], acc);
-                        Qu[i] += acc;
+                        const int e = t - oQuu, i = e / m, j = e - i * m;
+                        Quu[e] = gather(t, k, (i == j) ? P.dt * Rd[i] : 0.0);
                     }
                 }
                 gsync<T>();
-                // P3: Cholesky of Quu + rho I (left-looking, lower), diagonal kept in ldiag
-                for (int e = tid; e < m * m; e += T) {
-                    int i = e / m, j = e - i * m;
-                    L[e] = Quu[e] + ((i == j) ? rho : 0.0);
+                ALTRO_TICK(0);
+                // P2: [Qxx | Qx] += A'[SA | s],  Qux = B'SA,  [Quu | Qu] += B'[SB | s]   (chains start from the
+                //     cost + AL expansion already in Qxx / Qx / Quu / Qu)
+                const int nt_xx = tn * tn1, nt_ux = tm * tn, nt_uu = tm * tm1;
+                for (int t = warp; t < nt_xx + nt_ux + nt_uu; t += NW) {
+                    if (t < nt_xx) {
+                        const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
+                        const int i = r0 + fr, j = c0 + fc;
+                        double d0 = (i < n) ? (j < n ? Qxx[i * n + j] : (j == n ? Qx[i] : 0.0)) : 0.0;
+                        double d1 = (i < n) ? (j + 1 < n ? Qxx[i * n + j + 1] : (j + 1 == n ? Qx[i] : 0.0)) : 0.0;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? A[l * n + ii] : 0.0; },
+                                  [&](int l, int jj) {
+                                      jj += c0;
+                                      const double *p = jj < n ? SA + l * n + jj : s + l;
+                                      return (l < n && jj <= n) ? *p : 0.0;
+                                  });
+                        if (i < n) {
+                            if (j < n) Qxx[i * n + j] = d0; else if (j == n) Qx[i] = d0;
+                            if (j + 1 < n) Qxx[i * n + j + 1] = d1; else if (j + 1 == n) Qx[i] = d1;
+                        }
+                    } else if (t < nt_xx + nt_ux) {
+                        const int u = t - nt_xx, r0 = (u / tn) << 3, c0 = (u % tn) << 3;
+                        const int i = r0 + fr, j = c0 + fc;
+                        double d0 = 0.0, d1 = 0.0;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
+                                  [&](int l, int jj) { jj += c0; return (l < n && jj < n) ? SA[l * n + jj] : 0.0; });
+                        if (i < m) {
+                            if (j < n) Qux[i * n + j] = d0;
+                            if (j + 1 < n) Qux[i * n + j + 1] = d1;
+                        }
+                    } else {
+                        const int u = t - nt_xx - nt_ux, r0 = (u / tm1) << 3, c0 = (u % tm1) << 3;
+                        const int i = r0 + fr, j = c0 + fc;
+                        double d0 = (i < m) ? (j < m ? Quu[i * m + j] : (j == m ? Qu[i] : 0.0)) : 0.0;
+                        double d1 = (i < m) ? (j + 1 < m ? Quu[i * m + j + 1] : (j + 1 == m ? Qu[i] : 0.0)) : 0.0;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
+                                  [&](int l, int jj) {
+                                      jj += c0;
+                                      const double *p = jj < m ? SB + l * m + jj : s + l;
+                                      return (l < n && jj <= m) ? *p : 0.0;
+                                  });
+                        if (i < m) {  // L = Quu + rho I: regularised copy for the factorisation
+                            if (j < m) { Quu[i * m + j] = d0; L[i * m + j] = d0 + ((i == j) ? rho : 0.0); }
+                            else if (j == m) Qu[i] = d0;
+                            if (j + 1 < m) { Quu[i * m + j + 1] = d1; L[i * m + j + 1] = d1 + ((i == j + 1) ? rho : 0.0); }
+                            else if (j + 1 == m) Qu[i] = d1;
+                        }
+                    }
                 }
                 gsync<T>();
+                ALTRO_TICK(2);
+                // P3: LDL' of Quu + rho I, kept as the un-normalised lower factor X (L = X diag(r)) and the
+                //     reciprocal pivots r = 1/D, so that there is one division per column and none per entry.
+                //     m <= 32: warp 0 alone, one lane per row, __syncwarp between columns.
                 bool bad = false;
-                for (int j = 0; j < m; ++j) {
-                    for (int i = j + tid; i < m; i += T) {
-                        double acc = L[i * m + j];
-                        for (int l = 0; l < j; ++l) acc = fma(-L[i * m + l], L[j * m + l], acc);
-                        L[i * m + j] = acc;
+                if (m <= 32) {
+                    if (warp == 0) {
+                        double rprev = 0.0;  // reciprocal pivot of the previous column (linv[j-1] is still in flight)
+                        for (int j = 0; j < m; ++j) {
+                            if (lane >= j && lane < m) {
+                                double acc = L[lane * m + j];
+                                for (int l = 0; l < j; ++l)
+                                    acc = fma(-L[lane * m + l], L[j * m + l] * (l == j - 1 ? rprev : linv[l]), acc);
+                                L[lane * m + j] = acc;
+                            }
+                            __syncwarp();
+                            const double piv = L[j * m + j];
+                            if (!(piv > 0.0)) { bad = true; break; }
+                            rprev = 1.0 / piv;
+                            if (lane == 0) linv[j] = rprev;
+                        }
+                        if (lane == 0) bc[5] = bad ? 1.0 : 0.0;
                     }
                     gsync<T>();
-                    double dsum = L[j * m + j];
-                    if (!(dsum > 0.0)) { bad = true; break; }  // same value in every thread
-                    double dj = sqrt(dsum);
-                    for (int i = j + 1 + tid; i < m; i += T) L[i * m + j] = L[i * m + j] / dj;
-                    if (tid == 0) ldiag[j] = dj;
-                    gsync<T>();
+                    bad = bc[5] != 0.0;
+                } else {
+                    for (int j = 0; j < m; ++j) {
+                        for (int i = j + tid; i < m; i += T) {
+                            double acc = L[i * m + j];
+                            for (int l = 0; l < j; ++l) acc = fma(-L[i * m + l], L[j * m + l] * linv[l], acc);
+                            L[i * m + j] = acc;
+                        }
+                        gsync<T>();
+                        const double piv = L[j * m + j];
+                        if (!(piv > 0.0)) { bad = true; break; }  // same value in every thread
+                        if (tid == 0) linv[j] = 1.0 / piv;
+                        gsync<T>();
+                    }
                 }
                 if (bad) { restart = true; break; }
-                // P4: K = -(L L')^-1 Qux, d = -(L L')^-1 Qu ; one right-hand side per thread
+                ALTRO_TICK(3);
+                // P4: [K | d] = -(Quu + rho I)^-1 [Qux | Qu] by forward / backward substitution, one (row, column)
+                //     entry per thread, all columns advancing together, one barrier per elimination step.
+                //     Forward: y = L^-1 b (consumers rescale y_l by r_l themselves), z = D^-1 y;
+                //     backward: x_i = z_i - r_i sum_{q>i} X[q][i] x_q, the sums accumulated in T1 | t1.
                 double *Kk = K + k * m * n, *dk_ = dv + k * m;
-                for (int c = tid; c <= n; c += T) {
-                    double *b = (c < n) ? Kk + c : dk_;
-                    const double *src = (c < n) ? Qux + c : Qu;
-                    const int st = (c < n) ? n : 1;
-                    for (int i = 0; i < m; ++i) {
-                        double acc = -src[i * st];
-                        for (int l = 0; l < i; ++l) acc = fma(-L[i * m + l], b[l * st], acc);
-                        b[i * st] = acc / ldiag[i];
+                const int ntask = m * (n + 1);
+                for (int e = tid; e < ntask; e += T) {  // b = -[Qux | Qu], backward accumulators = 0
+                    const int i = e / (n + 1), c = e - i * (n + 1);
+                    if (c < n) { Kk[i * n + c] = -Qux[i * n + c]; T1[i * n + c] = 0.0; }
+                    else { dk_[i] = -Qu[i]; t1[i] = 0.0; }
+                }
+                gsync<T>();
+                for (int l = 0; l < m - 1; ++l) {
+                    const double rl = linv[l];
+                    for (int e = tid; e < ntask; e += T) {
+                        const int i = e / (n + 1), c = e - i * (n + 1);
+                        if (i > l) {
+                            double *bi = (c < n) ? Kk + i * n + c : dk_ + i;
+                            const double yl = (c < n) ? Kk[l * n + c] : dk_[l];
+                            *bi = fma(-L[i * m + l], yl * rl, *bi);
+                        }
                     }
-                    for (int i = m - 1; i >= 0; --i) {
-                        double acc = b[i * st];
-                        for (int l = i + 1; l < m; ++l) acc = fma(-L[l * m + i], b[l * st], acc);
-                        b[i * st] = acc / ldiag[i];
+                    gsync<T>();
+                }
+                for (int e = tid; e < ntask; e += T) {  // z = y r
+                    const int i = e / (n + 1), c = e - i * (n + 1);
+                    double *bi = (c < n) ? Kk + i * n + c : dk_ + i;
+                    *bi = *bi * linv[i];
+                }
+                gsync<T>();
+                for (int l = m - 1; l >= 1; --l) {
+                    const double rl = linv[l];
+                    for (int e = tid; e < ntask; e += T) {
+                        const int i = e / (n + 1), c = e - i * (n + 1);
+                        if (i < l) {
+                            const double zl = (c < n) ? Kk[l * n + c] : dk_[l];
+                            const double sl = (c < n) ? T1[l * n + c] : t1[l];
+                            double *ai = (c < n) ? T1 + i * n + c : t1 + i;
+                            *ai = fma(L[l * m + i], fma(-rl, sl, zl), *ai);  // x_l recomputed by every consumer
+                        }
+                    }
+                    gsync<T>();
+                }
+                for (int e = tid; e < ntask; e += T) {  // x_i = z_i - r_i acc_i
+                    const int i = e / (n + 1), c = e - i * (n + 1);
+                    double *bi = (c < n) ? Kk + i * n + c : dk_ + i;
+                    const double acc2 = (c < n) ? T1[i * n + c] : t1[i];
+                    *bi = fma(-linv[i], acc2, *bi);
+                }
+                gsync<T>();
+                ALTRO_TICK(4);
+                // P5: [T1 | t1] = Quu [K | d] + [Qux | Qu]
+                for (int t = warp; t < tm * tn1; t += NW) {
+                    const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
+                    const int i = r0 + fr, j = c0 + fc;
+                    double d0 = (i < m) ? (j < n ? Qux[i * n + j] : (j == n ? Qu[i] : 0.0)) : 0.0;
+                    double d1 = (i < m) ? (j + 1 < n ? Qux[i * n + j + 1] : (j + 1 == n ? Qu[i] : 0.0)) : 0.0;
+                    mma_chain(d0, d1, m,
+                              [&](int ii, int l) { ii += r0; return (ii < m && l < m) ? Quu[ii * m + l] : 0.0; },
+                              [&](int l, int jj) {
+                                  jj += c0;
+                                  const double *p = jj < n ? Kk + l * n + jj : dk_ + l;
+                                  return (l < m && jj <= n) ? *p : 0.0;
+                              });
+                    __syncwarp();
+                    if (i < m) {
+                        if (j < n) T1[i * n + j] = d0; else if (j == n) t1[i] = d0;
+                        if (j + 1 < n) T1[i * n + j + 1] = d1; else if (j + 1 == n) t1[i] = d1;
                     }
                 }
                 gsync<T>();
-                // P5: T1 = Quu K + Qux, t1 = Quu d + Qu
-                for (int e = tid; e < m * n + m; e += T) {
-                    if (e < m * n) {
-                        int i = e / n, j = e - i * n;
-                        double acc = Qux[e];
-                        for (int l = 0; l < m; ++l) acc = fma(Quu[i * m + l], Kk[l * n + j], acc);
-                        T1[e] = acc;
-                    } else {
-                        int i = e - m * n;
-                        double acc = Qu[i];
-                        for (int l = 0; l < m; ++l) acc = fma(Quu[i * m + l], dk_[l], acc);
-                        t1[i] = acc;
-                    }
-                }
-                gsync<T>();
-                // P6: S' = Qxx + K'T1 + Qux'K (into SA), s = Qx + K't1 + Qux'd, dV += [d'Qu, 1/2 d'Quu d]
-                for (int e = tid; e < n * n + n; e += T) {
-                    if (e < n * n) {
-                        int i = e / n, j = e - i * n;
-                        double acc = Qxx[e];
-                        for (int l = 0; l < m; ++l) acc = fma(Kk[l * n + i], T1[l * n + j], acc);
-                        for (int l = 0; l < m; ++l) acc = fma(Qux[l * n + i], Kk[l * n + j], acc);
-                        SA[e] = acc;
-                    } else {
-                        int i = e - n * n;
-                        double acc = Qx[i];
-                        for (int l = 0; l < m; ++l) acc = fma(Kk[l * n + i], t1[l], acc);
-                        for (int l = 0; l < m; ++l) acc = fma(Qux[l * n + i], dk_[l], acc);
-                        s[i] = acc;
+                ALTRO_TICK(5);
+                // P6: [S' | s] = [Qxx | Qx] + K'[T1 | t1] + Qux'[K | d]; the transposed tile is chained in the same
+                //     lanes so that S = (S' + S'^T)/2 needs no second pass.  dV += [d'Qu, 1/2 d'Quu d].
+                for (int t = warp; t < tn * tn1; t += NW) {
+                    const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
+                    const int i = r0 + fr, j = c0 + fc;
+                    double d0 = (i < n) ? (j < n ? Qxx[i * n + j] : (j == n ? Qx[i] : 0.0)) : 0.0;
+                    double d1 = (i < n) ? (j + 1 < n ? Qxx[i * n + j + 1] : (j + 1 == n ? Qx[i] : 0.0)) : 0.0;
+                    double e0 = (i < n && j < n) ? Qxx[j * n + i] : 0.0;
+                    double e1 = (i < n && j + 1 < n) ? Qxx[(j + 1) * n + i] : 0.0;
+                    auto Kt = [&](int ii, int l) { ii += r0; return (ii < n && l < m) ? Kk[l * n + ii] : 0.0; };
+                    auto Qt = [&](int ii, int l) { ii += r0; return (ii < n && l < m) ? Qux[l * n + ii] : 0.0; };
+                    auto Tt = [&](int ii, int l) { ii += r0; return (ii < n && l < m) ? T1[l * n + ii] : 0.0; };
+                    auto T1c = [&](int l, int jj) {
+                        jj += c0;
+                        const double *p = jj < n ? T1 + l * n + jj : t1 + l;
+                        return (l < m && jj <= n) ? *p : 0.0;
+                    };
+                    auto Kc = [&](int l, int jj) {
+                        jj += c0;
+                        const double *p = jj < n ? Kk + l * n + jj : dk_ + l;
+                        return (l < m && jj <= n) ? *p : 0.0;
+                    };
+                    auto Kn = [&](int l, int jj) { jj += c0; return (l < m && jj < n) ? Kk[l * n + jj] : 0.0; };
+                    auto Qn = [&](int l, int jj) { jj += c0; return (l < m && jj < n) ? Qux[l * n + jj] : 0.0; };
+                    mma_chain(d0, d1, m, Kt, T1c);  // + K' T1
+                    mma_chain(d0, d1, m, Qt, Kc);   // + Qux' K
+                    mma_chain(e0, e1, m, Tt, Kn);   // transposed: + T1' K  (= (K'T1)' element for element)
+                    mma_chain(e0, e1, m, Kt, Qn);   //             + K' Qux
+                    if (i < n) {
+                        if (j < n) S[i * n + j] = 0.5 * (d0 + e0); else if (j == n) s[i] = d0;
+                        if (j + 1 < n) S[i * n + j + 1] = 0.5 * (d1 + e1); else if (j + 1 == n) s[i] = d1;
                     }
                 }
                 if (tid == T - 1) {
@@ -713,12 +860,7 @@ struct Ctx {
                     }
                 }
                 gsync<T>();
-                // P7: symmetrise
-                for (int e = tid; e < n * n; e += T) {
-                    int i = e / n, j = e - i * n;
-                    S[e] = 0.5 * (SA[e] + SA[j * n + i]);
-                }
-                gsync<T>();
+                ALTRO_TICK(6);
             }
             if (restart) {
                 reg_increase(rho, drho);
@@ -796,10 +938,14 @@ struct Ctx {
                 rho += P.o.bp_reg_fp;
                 break;
             }
+            const long long cr = clock64();
             bool ok = rollout_alpha(alpha);
+            ph_roll += clock64() - cr;
             ++trials;
             if (!ok) { ++iter; alpha *= 0.5; continue; }
+            const long long cc = clock64();
             J = al_cost(Xb, Ub);
+            ph_cost += clock64() - cc;
             double expected = -alpha * (dV1 + alpha * dV2);
             z = expected > 0.0 ? (J_prev - J) / expected : -1.0;
             ++iter;
@@ -882,6 +1028,8 @@ struct Ctx {
     __device__ void solve_core(int slot)
     {
         const altro_opts_t &o = P.o;
+        long long ph[4] = {0, 0, 0, 0};
+        const long long cs = clock64();
         int iters = 0, outer_done = 0, status = ALTRO_UNSOLVED, trials = 0;
         double cmax = INFINITY, J = 0.0, pen_max = 0.0;
         for (int outer = 1; outer <= o.iterations_outer; ++outer) {
@@ -891,13 +1039,19 @@ struct Ctx {
             const double gtol = last ? o.gradient_tolerance : o.gradient_tolerance_intermediate;
             double rho = o.bp_reg_initial, drho = 0.0;
             int dJ_zero = 0;
+            long long c0 = clock64();
             rollout_open_loop();
             double J_prev = al_cost(X, U);
             J = J_prev;
+            ph[0] += clock64() - c0;
             for (int it = 0; it < o.iterations_inner; ++it) {
                 double dV1, dV2;
+                c0 = clock64();
                 if (!backward_pass(rho, drho, dV1, dV2)) { status = ALTRO_NOT_PD; break; }
+                long long c1 = clock64();
+                ph[1] += c1 - c0;
                 J = forward_pass(dV1, dV2, J_prev, rho, drho, trials);
+                ph[2] += clock64() - c1;
                 if (J > o.max_cost_value || !(J == J)) { status = ALTRO_MAXIMUM_COST; break; }
                 copy_traj(X, U, Xb, Ub);
                 double dJ = fabs(J - J_prev);
@@ -942,6 +1096,13 @@ struct Ctx {
             P.cost_al[at] = J;
             P.cmax[at] = cmax;
             P.penmax[at] = pen_max;
+            if (P.phase) {  // cycles: initial rollout+cost, backward pass (incl. expansion), forward pass, whole solve
+                long long *pp = P.phase + (size_t)inst * 8;
+                if (!P.phase_detail) { pp[0] += ph[0]; pp[1] += ph[1]; pp[2] += ph[2]; pp[3] += clock64() - cs; }
+                if (P.phase_detail) { for (int q = 0; q < 7; ++q) { pp[q] += bpc[q]; bpc[q] = 0; } pp[7] += iters; }
+                else { pp[4] += ph_exp; pp[5] += ph_roll; pp[6] += ph_cost; }
+                ph_exp = ph_roll = ph_cost = 0;
+            }
         }
     }
 

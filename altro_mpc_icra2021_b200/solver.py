@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "altro_set_options", "altro_set_dynamics", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint",
     "altro_update_constraint_data", "altro_set_x0", "altro_set_trajectory", "altro_get_trajectory", "altro_dual_len",
     "altro_set_duals", "altro_get_duals", "altro_shift_fill", "altro_solve", "altro_sync", "altro_get_stats",
-    "altro_get_timing", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0", "altro_mpc_run",
+    "altro_get_timing", "altro_get_phase_cycles", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0", "altro_mpc_run",
     "altro_get_run_results",
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
     "altro_measure_peaks",
@@ -341,6 +341,12 @@ class ALTROSolver:
     def get_trace(self) -> np.ndarray:
         out = np.zeros((self.prob.B, self._trace_rows, 10))
         self._ck(self.lib.altro_get_trace(self.h, _p(out)))
+        return out
+
+    def phase_cycles(self, enable: bool = True) -> np.ndarray:
+        """Per-instance cycle counters per solver phase since the last call (see altro_get_phase_cycles)."""
+        out = np.zeros((self.prob.B, 8), np.int64)
+        self._ck(self.lib.altro_get_phase_cycles(self.h, int(enable), _p(out)))
         return out
 
     def launch_info(self) -> dict:

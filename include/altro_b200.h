@@ -133,6 +133,11 @@ int altro_get_timing(altro_handle_t h, double *device_ms, long long *per_instanc
 int altro_set_trace(altro_handle_t h, int max_rows);
 int altro_get_trace(altro_handle_t h, double *out /* [B][max_rows][10] */);
 
+/* Profiling aid: SM-clock cycles per instance accumulated since enabling, out[B][8] = {initial rollout + cost,
+ * backward pass incl. expansion, forward pass, whole solve, expansion, line-search rollouts, line-search costs, 0}.
+ * enable != 0 (re)starts the counters after the optional read; enable == 0 stops them. */
+int altro_get_phase_cycles(altro_handle_t h, int enable, long long *out);
+
 /* benchmark_solve!(solver) restore-and-resolve semantics (random_linear_problem.jl:161):
  * snapshot / restore of (X, U, duals) on the device. */
 int altro_snapshot(altro_handle_t h);

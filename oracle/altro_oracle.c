@@ -535,12 +535,14 @@ restart:;
         for (int i = 0; i < m; ++i) w->Qu[i] = dt * pb->R[i] * (w->U[(size_t)k * m + i] - ur[i]);
         scatter_expansion(pb, w, k, ORC_STATE, w->Qx, w->Qxx, n);
         scatter_expansion(pb, w, k, ORC_CONTROL, w->Qu, w->Quu, m);
-        /* action-value expansion (_calc_Q!): Qxx += A'SA, Qux = B'SA, Quu += B'SB, Qx += A's, Qu += B's */
+        /* action-value expansion (_calc_Q!): Qxx += A'SA, Qux = B'SA, Quu += B'SB, Qx += A's, Qu += B's.
+         * Every chain starts from the value it accumulates into and runs over l ascending: this is exactly
+         * what the kernel's FP64 tensor-core tiles (mma.sync m8n8k4) compute. */
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) {
-                double acc = 0.0;
+                double acc = w->Qxx[i * n + j];
                 for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], w->SA[l * n + j], acc);
-                w->Qxx[i * n + j] += acc;
+                w->Qxx[i * n + j] = acc;
             }
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < n; ++j) {
@@ -550,42 +552,42 @@ restart:;
             }
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < m; ++j) {
-                double acc = 0.0;
+                double acc = w->Quu[i * m + j];
                 for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], w->SB[l * m + j], acc);
-                w->Quu[i * m + j] += acc;
+                w->Quu[i * m + j] = acc;
             }
         for (int i = 0; i < n; ++i) {
-            double acc = 0.0;
+            double acc = w->Qx[i];
             for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], w->s[l], acc);
-            w->Qx[i] += acc;
+            w->Qx[i] = acc;
         }
         for (int i = 0; i < m; ++i) {
-            double acc = 0.0;
+            double acc = w->Qu[i];
             for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + i], w->s[l], acc);
-            w->Qu[i] += acc;
+            w->Qu[i] = acc;
         }
-        /* control regularisation (_bp_reg!, :control) and left-looking Cholesky of Quu + rho I */
+        /* control regularisation (_bp_reg!, :control) and LDL' of Quu + rho I, kept as the un-normalised lower
+         * factor X (L = X diag(r)) and reciprocal pivots r = 1/D: one division per column. */
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < m; ++j) w->L[i * m + j] = w->Quu[i * m + j] + ((i == j) ? *rho : 0.0);
         int bad = 0;
         for (int j = 0; j < m && !bad; ++j) {
             for (int i = j; i < m; ++i) {
                 double acc = w->L[i * m + j];
-                for (int l = 0; l < j; ++l) acc = fma(-w->L[i * m + l], w->L[j * m + l], acc);
+                for (int l = 0; l < j; ++l) acc = fma(-w->L[i * m + l], w->L[j * m + l] * w->ldiag[l], acc);
                 w->L[i * m + j] = acc;
             }
-            double dsum = w->L[j * m + j];
-            if (!(dsum > 0.0)) { bad = 1; break; }
-            double dj = sqrt(dsum);
-            for (int i = j + 1; i < m; ++i) w->L[i * m + j] = w->L[i * m + j] / dj;
-            w->ldiag[j] = dj;
+            double piv = w->L[j * m + j];
+            if (!(piv > 0.0)) { bad = 1; break; }
+            w->ldiag[j] = 1.0 / piv; /* reciprocal pivot r_j */
         }
         if (bad) {
             reg_increase(o, rho, drho);
             if (*rho > o->bp_reg_max) return 1;
             goto restart;
         }
-        /* gains (_calc_gains!): K = -(L L')^-1 Qux, d = -(L L')^-1 Qu */
+        /* gains (_calc_gains!): [K | d] = -(Quu + rho I)^-1 [Qux | Qu]:
+         * forward y = L^-1 b, z = D^-1 y = y r;  backward x_i = z_i - r_i sum_{q>i} X[q][i] x_q (q descending) */
         double *K = w->K + (size_t)k * m * n, *dv = w->dv + (size_t)k * m;
         for (int c = 0; c <= n; ++c) {
             double *b = (c < n) ? K + c : dv;
@@ -593,13 +595,14 @@ restart:;
             const int st = (c < n) ? n : 1;
             for (int i = 0; i < m; ++i) {
                 double acc = -src[i * st];
-                for (int l = 0; l < i; ++l) acc = fma(-w->L[i * m + l], b[l * st], acc);
-                b[i * st] = acc / w->ldiag[i];
+                for (int l = 0; l < i; ++l) acc = fma(-w->L[i * m + l], b[l * st] * w->ldiag[l], acc);
+                b[i * st] = acc; /* y_i */
             }
+            for (int i = 0; i < m; ++i) b[i * st] = b[i * st] * w->ldiag[i]; /* z_i */
             for (int i = m - 1; i >= 0; --i) {
-                double acc = b[i * st];
-                for (int l = i + 1; l < m; ++l) acc = fma(-w->L[l * m + i], b[l * st], acc);
-                b[i * st] = acc / w->ldiag[i];
+                double acc2 = 0.0;
+                for (int l = m - 1; l > i; --l) acc2 = fma(w->L[l * m + i], b[l * st], acc2);
+                b[i * st] = fma(-w->ldiag[i], acc2, b[i * st]);
             }
         }
         /* cost-to-go (_calc_ctg!), unregularised Quu:  T1 = Quu K + Qux,  t1 = Quu d + Qu */
