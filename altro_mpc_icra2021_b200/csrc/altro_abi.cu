@@ -47,7 +47,10 @@ struct altro_handle_s {
     // cost / reference / state
     double *Q = nullptr, *R = nullptr, *Qf = nullptr, *xref = nullptr, *uref = nullptr, *x0 = nullptr;
     double *X = nullptr, *U = nullptr, *lam = nullptr;
-    double *X_snap = nullptr, *U_snap = nullptr, *lam_snap = nullptr;
+    double *X_snap = nullptr, *U_snap = nullptr, *lam_snap = nullptr, *x0_snap = nullptr, *xref_snap = nullptr,
+           *uref_snap = nullptr;
+    int *kidx_snap = nullptr;
+    int bank_pos_snap = 0;
     // stats
     int *iters = nullptr, *outer = nullptr, *status = nullptr, *trials = nullptr;
     double *cost = nullptr, *cost_al = nullptr, *cmax = nullptr, *penmax = nullptr;
@@ -66,7 +69,7 @@ struct altro_handle_s {
     // MPC track
     double *trackX = nullptr, *trackU = nullptr, *noise = nullptr, *noise_bank = nullptr;
     int *kidx = nullptr;
-    int Nt = 0, bank_steps = 0, bank_pos = 0, noise_mode = 0;
+    int Nt = 0, bank_steps = 0, bank_pos = 0, bank_cap = 0, noise_mode = 0;
     double noise_w1 = 1.0, noise_w2 = 1.0;
     // launch
     int threads_req = 0, threads = 0, smem = 0, regs = 0, ctas_per_sm = 0, num_sms = 0, dyn_in_smem = 0, ref_in_smem = 1;
@@ -268,7 +271,7 @@ int finalize(altro_handle_t h)
         dsc.per_knot = c.per_knot; dsc.per_instance = c.per_instance; dsc.rowsparse = c.rowsparse;
         dsc.dual_off = P;
         dsc.ex_off = EX;
-        dsc.ex_stride = c.rowsparse ? 2 * c.w : c.w + c.w * c.w;
+        dsc.ex_stride = c.rowsparse ? 2 * c.w : c.w + c.w * (c.w + 1) / 2;
         dsc.tgt_off = TG;
         TG += dsc.ex_stride;
         // gather sources: (block, offset inside the block's per-knot expansion) for every target it touches
@@ -279,8 +282,10 @@ int finalize(altro_handle_t h)
             for (int e = 0; e < c.w; ++e) srcs[omat + c.inds[e] * ld + c.inds[e]].push_back(((int)i << 16) | (c.w + e));
         } else {
             for (int a = 0; a < c.w; ++a)
-                for (int b = 0; b < c.w; ++b)
-                    srcs[omat + c.inds[a] * ld + c.inds[b]].push_back(((int)i << 16) | (c.w + a * c.w + b));
+                for (int b = 0; b < c.w; ++b) {  // upper-triangle packed storage of the symmetric block
+                    const int lo = std::min(a, b), hi = std::max(a, b);
+                    srcs[omat + c.inds[a] * ld + c.inds[b]].push_back(((int)i << 16) | (c.w + lo * c.w - lo * (lo - 1) / 2 + (hi - lo)));
+                }
         }
         dsc.G = c.G_dev; dsc.h = c.h_dev; dsc.rs_col = c.rs_col_dev; dsc.rs_coef = c.rs_coef_dev;
         for (int j = 0; j < c.w; ++j) dsc.inds[j] = c.inds[j];
@@ -312,9 +317,11 @@ int finalize(altro_handle_t h)
     if (T != 32 && T != 64 && T != 128 && T != 256) return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 32, 64, 128 or 256");
     h->threads = T;
     h->dyn_in_smem = (!h->dyn_per_knot && !h->dyn_per_instance) ? 1 : 0;
-    h->ref_in_smem = 1;
-    size_t smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 1, T, h->ITAB);
-    if (smem > (size_t)prop.sharedMemPerBlockOptin) {  // long horizons: keep the reference in global memory
+    // the reference window lives in shared memory unless a track is registered (closed-loop runs read the
+    // window straight from the shared, L2-resident track) or the horizon is too long
+    h->ref_in_smem = h->trackX ? 0 : 1;
+    size_t smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, h->ref_in_smem, T, h->ITAB);
+    if (smem > (size_t)prop.sharedMemPerBlockOptin && h->ref_in_smem) {  // long horizons: keep the reference in global memory
         h->ref_in_smem = 0;
         smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 0, T, h->ITAB);
     }
@@ -433,6 +440,8 @@ int altro_create(altro_handle_t *out, int device, int n, int m, int N, int batch
     CKC(dalloc(&h->xref, B * N * n)); CKC(dalloc(&h->uref, B * (N - 1) * m)); CKC(dalloc(&h->x0, B * n));
     CKC(dalloc(&h->X, B * N * n)); CKC(dalloc(&h->U, B * (N - 1) * m));
     CKC(dalloc(&h->X_snap, B * N * n)); CKC(dalloc(&h->U_snap, B * (N - 1) * m));
+    CKC(dalloc(&h->x0_snap, B * n)); CKC(dalloc(&h->xref_snap, B * N * n)); CKC(dalloc(&h->uref_snap, B * (N - 1) * m));
+    CKC(dalloc(&h->kidx_snap, B));
     CKC(dalloc(&h->iters, B)); CKC(dalloc(&h->outer, B)); CKC(dalloc(&h->status, B)); CKC(dalloc(&h->trials, B));
     CKC(dalloc(&h->cost, B)); CKC(dalloc(&h->cost_al, B)); CKC(dalloc(&h->cmax, B)); CKC(dalloc(&h->penmax, B));
     CKC(dalloc(&h->t_ns, B)); CKC(dalloc(&h->noise, B * n)); CKC(dalloc(&h->kidx, B));
@@ -447,7 +456,7 @@ int altro_destroy(altro_handle_t h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
-                    h->U_snap, h->lam_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
+                    h->U_snap, h->lam_snap, h->x0_snap, h->xref_snap, h->uref_snap, h->kidx_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
                     h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -757,8 +766,6 @@ int altro_mpc_run(altro_handle_t h, int steps, int shift)
     int rc = finalize(h);
     if (rc) return rc;
     if (steps < 1) return fail(h, ALTRO_ERR_INVALID, "steps must be >= 1");
-    if (!h->ref_in_smem && h->trackX)
-        return fail(h, ALTRO_ERR_UNSUPPORTED, "closed-loop runs need the reference window in shared memory (horizon too long)");
     rc = ensure_stat_capacity(h, steps);
     if (rc) return rc;
     h->have_x0 = true;
@@ -864,15 +871,28 @@ int altro_get_phase_cycles(altro_handle_t h, int enable, long long *out)
     return ALTRO_OK;
 }
 
+// (X, U, duals, x0, reference window, track index, noise-bank position): everything a closed-loop run mutates
+static int copy_state(altro_handle_t h, bool save)
+{
+    const size_t B = h->B, n = h->n, m = h->m, N = h->N;
+    struct { void *live, *snap; size_t bytes; } v[] = {
+        {h->X, h->X_snap, B * N * n * sizeof(double)},       {h->U, h->U_snap, B * (N - 1) * m * sizeof(double)},
+        {h->lam, h->lam_snap, B * std::max(h->P, 1) * sizeof(double)}, {h->x0, h->x0_snap, B * n * sizeof(double)},
+        {h->xref, h->xref_snap, B * N * n * sizeof(double)}, {h->uref, h->uref_snap, B * (N - 1) * m * sizeof(double)},
+        {h->kidx, h->kidx_snap, B * sizeof(int)}};
+    for (auto &e : v)
+        CK(h, cudaMemcpyAsync(save ? e.snap : e.live, save ? e.live : e.snap, e.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (save) h->bank_pos_snap = h->bank_pos;
+    else h->bank_pos = h->bank_pos_snap;
+    return ALTRO_OK;
+}
+
 int altro_snapshot(altro_handle_t h)
 {
     REQ(h);
     int rc = finalize(h);
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(h->X_snap, h->X, (size_t)h->B * h->N * h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->U_snap, h->U, (size_t)h->B * (h->N - 1) * h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->lam_snap, h->lam, (size_t)h->B * std::max(h->P, 1) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    return ALTRO_OK;
+    return copy_state(h, true);
 }
 
 int altro_restore(altro_handle_t h)
@@ -880,10 +900,7 @@ int altro_restore(altro_handle_t h)
     REQ(h);
     int rc = finalize(h);
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(h->X, h->X_snap, (size_t)h->B * h->N * h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->U, h->U_snap, (size_t)h->B * (h->N - 1) * h->m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->lam, h->lam_snap, (size_t)h->B * std::max(h->P, 1) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    return ALTRO_OK;
+    return copy_state(h, false);
 }
 
 int altro_set_track(altro_handle_t h, const double *tX, const double *tU, int Nt, const int *k_start)
@@ -891,10 +908,16 @@ int altro_set_track(altro_handle_t h, const double *tX, const double *tU, int Nt
     REQ(h);
     if (!tX || !tU || Nt < 2 || !k_start) return fail(h, ALTRO_ERR_INVALID, "bad track");
     if (h->trackX) { cudaFree(h->trackX); cudaFree(h->trackU); h->trackX = h->trackU = nullptr; }
-    CK(h, dalloc(&h->trackX, (size_t)Nt * h->n));
-    CK(h, dalloc(&h->trackU, (size_t)(Nt - 1) * h->m));
-    CK(h, cudaMemcpy(h->trackX, tX, (size_t)Nt * h->n * sizeof(double), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->trackU, tU, (size_t)(Nt - 1) * h->m * sizeof(double), cudaMemcpyHostToDevice));
+    // device copies padded with N repeats of the last knot, so that every N-knot window is one contiguous slice
+    std::vector<double> px((size_t)(Nt + h->N) * h->n), pu((size_t)(Nt - 1 + h->N) * h->m);
+    for (int k = 0; k < Nt + h->N; ++k)
+        memcpy(&px[(size_t)k * h->n], tX + (size_t)std::min(k, Nt - 1) * h->n, h->n * sizeof(double));
+    for (int k = 0; k < Nt - 1 + h->N; ++k)
+        memcpy(&pu[(size_t)k * h->m], tU + (size_t)std::min(k, Nt - 2) * h->m, h->m * sizeof(double));
+    CK(h, dalloc(&h->trackX, px.size()));
+    CK(h, dalloc(&h->trackU, pu.size()));
+    CK(h, cudaMemcpy(h->trackX, px.data(), px.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->trackU, pu.data(), pu.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(h->kidx, k_start, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice));
     h->Nt = Nt;
     return ALTRO_OK;
@@ -919,15 +942,22 @@ int altro_get_x0(altro_handle_t h, double *x0)
 int altro_set_noise_bank(altro_handle_t h, const double *noise, int steps)
 {
     REQ(h);
-    CK(h, cudaStreamSynchronize(h->stream));
-    if (h->noise_bank) { cudaFree(h->noise_bank); h->noise_bank = nullptr; }
-    h->bank_steps = h->bank_pos = 0;
-    if (!noise || steps < 1) return ALTRO_OK;
+    if (!noise || steps < 1) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (h->noise_bank) { cudaFree(h->noise_bank); h->noise_bank = nullptr; }
+        h->bank_steps = h->bank_pos = h->bank_cap = 0;
+        return ALTRO_OK;
+    }
     const size_t cnt = (size_t)steps * h->B * h->n;
-    CK(h, dalloc(&h->noise_bank, cnt));
-    CK(h, cudaMemcpy(h->noise_bank, noise, cnt * sizeof(double), cudaMemcpyHostToDevice));
+    if (steps > h->bank_cap) {  // grow only: repeated uploads of the same size reuse the allocation
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (h->noise_bank) { cudaFree(h->noise_bank); h->noise_bank = nullptr; }
+        CK(h, dalloc(&h->noise_bank, cnt));
+        h->bank_cap = steps;
+    }
     h->bank_steps = steps;
-    return ALTRO_OK;
+    h->bank_pos = 0;
+    return upload(h, h->noise_bank, noise, cnt);  // async on the handle's stream (DMA if the buffer is pinned)
 }
 
 int altro_mpc_transition(altro_handle_t h, const double *noise, int shift)

@@ -32,7 +32,7 @@ struct ConDesc {
     int rowsparse;  // every row of G has <= 1 nonzero (bounds): value = h[r] + rs_coef[r] * z[inds[rs_col[r]]]
     int dual_off;   // offset of the block in the per-instance dual vector
     int ex_off;     // offset of the block in the per-instance expansion scratch
-    int ex_stride;  // per-knot stride there: w + w*w (dense) or 2*w (row-sparse)
+    int ex_stride;  // per-knot stride there: w + w(w+1)/2 (dense, upper triangle) or 2*w (row-sparse)
     int tgt_off;    // offset of the block's scatter targets in the shared int table (ex_stride entries)
     const double *G, *h;
     const int *rs_col;
@@ -274,7 +274,7 @@ struct Ctx {
         for (int i = tid; i < P.P; i += T) gl[i] = lam[i];
         if (P.steps > 0) {  // closed-loop run: the handle's x0 and reference window follow the plant
             for (int i = tid; i < n; i += T) P.x0[(size_t)inst * n + i] = X[i];
-            if (P.trackX && P.ref_in_smem) {
+            if (P.trackX) {
                 double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
                 for (int i = tid; i < N * n; i += T) gxr[i] = xr[i];
                 for (int i = tid; i < (N - 1) * m; i += T) gur[i] = ur[i];
@@ -290,6 +290,7 @@ struct Ctx {
         if (c.rowsparse) return fma(c.rs_coef[r], z[c.inds[c.rs_col[r]]], h[r]);
         double acc = h[r];
         const double *g = G + r * c.w;
+#pragma unroll 1
         for (int j = 0; j < c.w; ++j) acc = fma(g[j], z[c.inds[j]], acc);
         return acc;
     }
@@ -479,12 +480,11 @@ struct Ctx {
                         for (int r = 0; r < p; ++r) acc = fma(G[r * w + j], y[r], acc);
                         g[j] = acc;
                     }
-                    for (int i = 0; i < w; ++i)
-                        for (int j = i; j < w; ++j) {
+                    for (int i = 0, at = 0; i < w; ++i)
+                        for (int j = i; j < w; ++j, ++at) {
                             double acc = 0.0;
                             for (int r = 0; r < p; ++r) acc = fma(G[r * w + i] * D[r], G[r * w + j], acc);
-                            H[i * w + j] = acc;
-                            H[j * w + i] = acc;
+                            H[at] = acc;
                         }
                 } else {
                     // lb = lam - mu c ; Pi(lb) ; g = -G' Pi(lb) ; H = mu G' dPi(lb) G  (structured)
@@ -497,19 +497,18 @@ struct Ctx {
                     const double t = lb[p - 1], a = sqrt(a2);
                     const double *gt = G + (p - 1) * w;
                     if (a <= -t) {
-                        for (int j = 0; j < w + w * w; ++j) g[j] = 0.0;
+                        for (int j = 0; j < c.ex_stride; ++j) g[j] = 0.0;
                     } else if (a <= t) {
                         for (int j = 0; j < w; ++j) {
                             double acc = 0.0;
                             for (int r = 0; r < p; ++r) acc = fma(G[r * w + j], lb[r], acc);
                             g[j] = -acc;
                         }
-                        for (int i = 0; i < w; ++i)
-                            for (int j = i; j < w; ++j) {
+                        for (int i = 0, at = 0; i < w; ++i)
+                            for (int j = i; j < w; ++j, ++at) {
                                 double acc = 0.0;
                                 for (int r = 0; r < p; ++r) acc = fma(G[r * w + i], G[r * w + j], acc);
-                                H[i * w + j] = mu_c * acc;
-                                H[j * w + i] = mu_c * acc;
+                                H[at] = mu_c * acc;
                             }
                     } else {
                         const double ia = 1.0 / a, cf = 0.5 * (1.0 + t * ia);
@@ -520,14 +519,12 @@ struct Ctx {
                             for (int r = 0; r < p - 1; ++r) acc = fma(G[r * w + j], lb[r], acc);
                             q[j] = acc * ia;  // omega_hat
                         }
-                        for (int i = 0; i < w; ++i)
-                            for (int j = i; j < w; ++j) {
+                        for (int i = 0, at = 0; i < w; ++i)
+                            for (int j = i; j < w; ++j, ++at) {
                                 double gg = 0.0;
                                 for (int r = 0; r < p - 1; ++r) gg = fma(G[r * w + i], G[r * w + j], gg);
                                 double qi = q[i] + gt[i], qj = q[j] + gt[j];
-                                double hv = mu_c * (cx * (gg - q[i] * q[j]) + 0.5 * qi * qj);
-                                H[i * w + j] = hv;
-                                H[j * w + i] = hv;
+                                H[at] = mu_c * (cx * (gg - q[i] * q[j]) + 0.5 * qi * qj);
                             }
                         for (int j = 0; j < w; ++j) g[j] = -cf * a * (q[j] + gt[j]);
                     }
@@ -997,8 +994,13 @@ struct Ctx {
         }
         if (P.trackX) {
             const int k0 = P.kidx[inst] + st + 1;
-            for (int i = tid; i < N * n; i += T) xr[i] = P.trackX[(size_t)min(k0 + i / n, P.Nt - 1) * n + i % n];
-            for (int i = tid; i < (N - 1) * m; i += T) ur[i] = P.trackU[(size_t)min(k0 + i / m, P.Nt - 2) * m + i % m];
+            if (P.ref_in_smem) {
+                for (int i = tid; i < N * n; i += T) xr[i] = P.trackX[(size_t)min(k0 + i / n, P.Nt - 1) * n + i % n];
+                for (int i = tid; i < (N - 1) * m; i += T) ur[i] = P.trackU[(size_t)min(k0 + i / m, P.Nt - 2) * m + i % m];
+            } else {  // the device track is padded with N copies of its last knot: the window is one contiguous slice
+                xr = const_cast<double *>(P.trackX) + (size_t)min(k0, P.Nt) * n;
+                ur = const_cast<double *>(P.trackU) + (size_t)min(k0, P.Nt - 1) * m;
+            }
         }
         if (P.shift) {
             // in-place left shifts in chunks of T: all reads of a chunk precede its writes, later chunks are untouched
@@ -1139,7 +1141,7 @@ struct Ctx {
 };
 
 template <int NX, int NU, int T>
-__global__ void __launch_bounds__(T) altro_solve_kernel(const __grid_constant__ Params P)
+__global__ void __launch_bounds__(T, 512 / T) altro_solve_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<NX, NU, T> ctx(P, smem_raw);

@@ -221,6 +221,13 @@ class ALTROSolver:
         self._results_stale = False
         return self.stats
 
+    def snapshot(self) -> None:
+        self.upload()
+        self._ck(self.lib.altro_snapshot(self.h))
+
+    def restore(self) -> None:
+        self._ck(self.lib.altro_restore(self.h))
+
     def sync(self) -> None:
         self._ck(self.lib.altro_sync(self.h))
 

@@ -139,7 +139,8 @@ int altro_get_trace(altro_handle_t h, double *out /* [B][max_rows][10] */);
 int altro_get_phase_cycles(altro_handle_t h, int enable, long long *out);
 
 /* benchmark_solve!(solver) restore-and-resolve semantics (random_linear_problem.jl:161):
- * snapshot / restore of (X, U, duals) on the device. */
+ * snapshot / restore, on the device, of everything a solve or a closed-loop run mutates: X, U, duals, x0, the
+ * reference window, the per-instance track index and the noise-bank position. */
 int altro_snapshot(altro_handle_t h);
 int altro_restore(altro_handle_t h);
 

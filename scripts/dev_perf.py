@@ -10,8 +10,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "rocket"
 B = int(os.environ.get("B", "4096")); K = int(os.environ.get("K", "20")); T = int(os.environ.get("T", "0"))
 wl = bench.Workload(name, B, 0xA1722, lambda p, o: S.ALTROSolver(p, o))
 sv = S.ALTROSolver(wl.prob, wl.opts, threads_per_instance=T)
-print(name, sv.launch_info())
 if wl.track is not None: sv.set_track(wl.track[0], wl.track[1], wl.k)
+print(name, sv.launch_info())
 sv.set_noise_model(*wl.noise_model); sv.set_noise_bank(wl.noise_samples(3 * K + 3))
 sv.solve()
 if wl.qstate is None:
