@@ -432,6 +432,9 @@ def main():
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     ps = np.array(per_step)
+    traffic = None
+    if wl.name == "rocket" and B == 4096 and fused:  # 18.75 MB per 20-step launch (ncu), state in+out once per launch
+        traffic = 18.75e6 * (0.5 + 0.5 * S_launch / 20.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * total_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -452,7 +455,9 @@ def main():
         "steps_per_launch": S_launch,
         "clocks": sampler.summary(),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["dfma_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["dfma_tflops"], "traffic": None,
+                     "frac": achieved / peaks["dfma_tflops"], "traffic": traffic,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the "
+                                     "20-step rocket launch (profiles/r1_summary.md), scaled to this launch's step count",
                      "peak_source": "DFMA stream measured live by altro_measure_peaks in this run "
                                     "(MEASURED_PEAKS.json has no FP64 figure); DMMA m8n8k4 peak "
                                     f"{peaks['dmma_tflops']:.1f} TFLOP/s",
