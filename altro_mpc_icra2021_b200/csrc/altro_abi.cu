@@ -44,6 +44,8 @@ struct altro_handle_s {
     int dyn_per_knot = 0, dyn_per_instance = 0;
     double *A = nullptr, *Bm = nullptr, *d = nullptr;
     size_t dyn_count = 0;
+    int dyn_slots = 0, sched_len = 0, step_abs = 0, step_abs_snap = 0;  // gait-scheduled models (quadruped)
+    int *sched = nullptr;
     // cost / reference / state
     double *Q = nullptr, *R = nullptr, *Qf = nullptr, *xref = nullptr, *uref = nullptr, *x0 = nullptr;
     double *X = nullptr, *U = nullptr, *lam = nullptr;
@@ -135,14 +137,16 @@ __global__ void shift_fill_kernel(int n, int m, int N, int P, int ncon, const Co
 // Noise models: 0 additive w1*z; 1 random-linear z*|x|_inf*w1 (random_linear_problem.jl:129);
 // 2 rocket: z*|x[0:n/2]|_2*w1 on positions, z*|x[n/2:n]|_2*w2 on velocities (simple_rocket.jl:63-70).
 __global__ void mpc_transition_kernel(int n, int m, int N, const double *A, const double *Bm, const double *d,
-                                      int dyn_per_knot, int dyn_per_instance, const double *X, const double *U,
+                                      int dyn_per_knot, int dyn_per_instance, const int *sched, int sched_len,
+                                      int dyn_slots, int step_abs, const double *X, const double *U,
                                       const double *noise, int noise_mode, double w1, double w2, double *x0,
                                       const double *trackX, const double *trackU, int Nt, int *kidx, double *xref,
                                       double *uref)
 {
     __shared__ double scale[2];
     const int inst = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const size_t base = dyn_per_instance ? (size_t)inst * (dyn_per_knot ? (size_t)(N - 1) : 1) : 0;
+    size_t base = dyn_per_instance ? (size_t)inst * (sched ? (size_t)dyn_slots : (dyn_per_knot ? (size_t)(N - 1) : 1)) : 0;
+    if (sched) base += sched[(size_t)inst * sched_len + min(step_abs, sched_len - N)];
     const double *A0 = A + base * n * n, *B0 = Bm + base * n * m, *d0 = d + base * n;
     const double *x = X + (size_t)inst * N * n, *u = U + (size_t)inst * (N - 1) * m;
     double *xo = x0 + (size_t)inst * n;
@@ -457,7 +461,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->x0_snap, h->xref_snap, h->uref_snap, h->kidx_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -516,6 +520,39 @@ int altro_set_dynamics(altro_handle_t h, int per_knot, int per_instance, const d
     int rc = upload(h, h->A, A, cnt * n * n);
     if (rc) return rc;
     rc = upload(h, h->Bm, Bm, cnt * n * m);
+    if (rc) return rc;
+    if (d) return upload(h, h->d, d, cnt * n);
+    CK(h, cudaMemsetAsync(h->d, 0, cnt * n * sizeof(double), h->stream));
+    return ALTRO_OK;
+}
+
+int altro_set_dynamics_slots(altro_handle_t h, int nslots, const double *A, const double *Bm, const double *d,
+                             const int *sched, int sched_len)
+{
+    REQ(h);
+    if (!A || !Bm || !sched || nslots < 1 || sched_len < h->N) return fail(h, ALTRO_ERR_INVALID, "bad dynamics schedule");
+    if (h->finalized && !h->sched) return fail(h, ALTRO_ERR_STATE, "dynamics layout cannot change after the first solve");
+    const size_t cnt = (size_t)h->B * nslots, n = h->n, m = h->m;
+    if (h->have_dyn && (cnt != h->dyn_count || !h->sched)) {
+        cudaFree(h->A); cudaFree(h->Bm); cudaFree(h->d);
+        h->A = h->Bm = h->d = nullptr;
+        h->have_dyn = false;
+    }
+    if (!h->have_dyn) {
+        CK(h, dalloc(&h->A, cnt * n * n));
+        CK(h, dalloc(&h->Bm, cnt * n * m));
+        CK(h, dalloc(&h->d, cnt * n));
+        h->dyn_count = cnt; h->dyn_per_knot = 1; h->dyn_per_instance = 1;
+        h->have_dyn = true;
+    }
+    if (h->sched && sched_len != h->sched_len) { cudaFree(h->sched); h->sched = nullptr; }
+    if (!h->sched) CK(h, dalloc(&h->sched, (size_t)h->B * sched_len));
+    h->dyn_slots = nslots; h->sched_len = sched_len;
+    for (size_t i = 0; i < (size_t)h->B * sched_len; ++i)
+        if (sched[i] < 0 || sched[i] >= nslots) return fail(h, ALTRO_ERR_INVALID, "schedule entry out of range");
+    CK(h, cudaMemcpyAsync(h->sched, sched, (size_t)h->B * sched_len * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    int rc = upload(h, h->A, A, cnt * n * n);
+    if (!rc) rc = upload(h, h->Bm, Bm, cnt * n * m);
     if (rc) return rc;
     if (d) return upload(h, h->d, d, cnt * n);
     CK(h, cudaMemsetAsync(h->d, 0, cnt * n * sizeof(double), h->stream));
@@ -724,6 +761,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     P.con = h->con_dev;
     P.itab = h->itab_dev;
     P.o = h->opts;
+    P.dyn_slots = h->dyn_slots; P.sched_len = h->sched_len; P.step0 = h->step_abs; P.dyn_sched = h->sched;
     P.steps = steps; P.shift = shift; P.noise_mode = h->noise_mode; P.Nt = h->Nt;
     P.noise_w1 = h->noise_w1; P.noise_w2 = h->noise_w2;
     if (steps > 0) {
@@ -744,6 +782,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     CK(h, cudaEventRecord(h->ev0, h->stream));
     CK(h, cudaLaunchKernel(h->kernel, dim3(h->B), dim3(h->threads), args, (size_t)h->smem, h->stream));
     CK(h, cudaEventRecord(h->ev1, h->stream));
+    h->step_abs += steps;
     if (steps > 0 && h->trackX) {
         advance_kidx_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->kidx, h->B, steps);
         CK(h, cudaGetLastError());
@@ -882,8 +921,8 @@ static int copy_state(altro_handle_t h, bool save)
         {h->kidx, h->kidx_snap, B * sizeof(int)}};
     for (auto &e : v)
         CK(h, cudaMemcpyAsync(save ? e.snap : e.live, save ? e.live : e.snap, e.bytes, cudaMemcpyDeviceToDevice, h->stream));
-    if (save) h->bank_pos_snap = h->bank_pos;
-    else h->bank_pos = h->bank_pos_snap;
+    if (save) { h->bank_pos_snap = h->bank_pos; h->step_abs_snap = h->step_abs; }
+    else { h->bank_pos = h->bank_pos_snap; h->step_abs = h->step_abs_snap; }
     return ALTRO_OK;
 }
 
@@ -975,10 +1014,12 @@ int altro_mpc_transition(altro_handle_t h, const double *noise, int shift)
         ++h->bank_pos;
     }
     mpc_transition_kernel<<<h->B, 64, 0, h->stream>>>(h->n, h->m, h->N, h->A, h->Bm, h->d, h->dyn_per_knot,
-                                                     h->dyn_per_instance, h->X, h->U, nz, h->noise_mode, h->noise_w1, h->noise_w2,
+                                                     h->dyn_per_instance, h->sched, h->sched_len, h->dyn_slots,
+                                                     h->step_abs, h->X, h->U, nz, h->noise_mode, h->noise_w1, h->noise_w2,
                                                      h->x0, h->trackX, h->trackU, h->Nt, h->kidx, h->xref, h->uref);
     CK(h, cudaGetLastError());
     h->have_x0 = true;
+    h->step_abs += 1;
     if (shift) return altro_shift_fill(h, 1, 1);
     return ALTRO_OK;
 }

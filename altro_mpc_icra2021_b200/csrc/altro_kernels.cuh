@@ -45,6 +45,10 @@ struct Params {
     int inst_offset;
     double dt;
     int dyn_per_knot, dyn_per_instance, dyn_in_smem, ref_in_smem;
+    // optional dynamics schedule (gait-scheduled LTV models, e.g. the quadruped): per instance `dyn_slots` models
+    // A[B][slots].., and knot k of MPC step s uses slot dyn_sched[inst][min(step0 + s + k, sched_len - 1)]
+    int dyn_slots, sched_len, step0;
+    const int *dyn_sched;
     const double *A, *Bm, *d;
     const double *Q, *R, *Qf;
     double *xref, *uref, *x0, *X, *U, *lam;
@@ -157,6 +161,7 @@ struct Ctx {
     ConDesc *cd;
     size_t dyn_base;
     int dyn_k;
+    const int *sched;  // this instance's dynamics schedule at the current MPC step, or nullptr
 
     __device__ Ctx(const Params &P_, unsigned char *raw) : P(P_)
     {
@@ -207,21 +212,31 @@ struct Ctx {
         NT = n + n * n + m + m * m;
         gptr = reinterpret_cast<int *>(cd + (ncon > 0 ? ncon : 1));
         gsrc = gptr + NT + 1;
-        dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_per_knot ? (size_t)(N - 1) : 1) : 0;
+        dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_sched ? (size_t)P.dyn_slots : (P.dyn_per_knot ? (size_t)(N - 1) : 1)) : 0;
         dyn_k = P.dyn_per_knot ? 1 : 0;
+        sched = nullptr;
+        set_step(0);
     }
 
+    __device__ __forceinline__ void set_step(int st)
+    {
+        if (P.dyn_sched) sched = P.dyn_sched + (size_t)inst * P.sched_len + min(P.step0 + st, P.sched_len - N);
+    }
+    __device__ __forceinline__ size_t dyn_index(int k) const
+    {
+        return dyn_base + (sched ? (size_t)sched[k] : (size_t)dyn_k * k);
+    }
     __device__ __forceinline__ const double *Ak(int k) const
     {
-        return P.dyn_in_smem ? sA : P.A + (dyn_base + (size_t)dyn_k * k) * n * n;
+        return P.dyn_in_smem ? sA : P.A + dyn_index(k) * n * n;
     }
     __device__ __forceinline__ const double *Bk(int k) const
     {
-        return P.dyn_in_smem ? sB : P.Bm + (dyn_base + (size_t)dyn_k * k) * n * m;
+        return P.dyn_in_smem ? sB : P.Bm + dyn_index(k) * n * m;
     }
     __device__ __forceinline__ const double *dk(int k) const
     {
-        return P.dyn_in_smem ? sd : P.d + (dyn_base + (size_t)dyn_k * k) * n;
+        return P.dyn_in_smem ? sd : P.d + dyn_index(k) * n;
     }
     __device__ __forceinline__ size_t con_idx(const ConDesc &c, int k) const
     {
@@ -606,8 +621,8 @@ struct Ctx {
                 long long tq = clock64(), tq2;
 #define ALTRO_TICK(slot) do { tq2 = clock64(); bpc[slot] += tq2 - tq; tq = tq2; } while (0)
                 if (!P.dyn_in_smem) {  // LTV: stage A_k, B_k into shared memory (coalesced), d_k is not needed here
-                    const double *gA = P.A + (dyn_base + (size_t)dyn_k * k) * n * n;
-                    const double *gB = P.Bm + (dyn_base + (size_t)dyn_k * k) * n * m;
+                    const double *gA = P.A + dyn_index(k) * n * n;
+                    const double *gB = P.Bm + dyn_index(k) * n * m;
                     for (int i = tid; i < n * n; i += T) sA[i] = gA[i];
                     for (int i = tid; i < n * m; i += T) sB[i] = gB[i];
                     gsync<T>();
@@ -1116,6 +1131,7 @@ struct Ctx {
         const int steps = P.steps > 0 ? P.steps : 1;
         for (int st = 0; st < steps; ++st) {
             if (P.steps > 0) {
+                set_step(st + 1);  // the window moves one knot forward with every transition
                 transition(st);
                 if (st > 0) {  // every solve! starts from reset penalties (and duals, if asked)
                     if (P.o.reset_duals)

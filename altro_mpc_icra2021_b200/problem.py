@@ -66,7 +66,10 @@ class LinearModel:
     per-instance LTV; `per_instance` disambiguates the two 3-D cases.
     """
 
-    def __init__(self, A, B, d=None, dt: float = 0.0, per_instance: Optional[bool] = None):
+    def __init__(self, A, B, d=None, dt: float = 0.0, per_instance: Optional[bool] = None, sched=None):
+        """`sched` (B, L) int32: gait-scheduled models -- A is (B, nslots, n, n) and knot k of the solve that follows
+        s transitions uses slot sched[i, s + k] (altro_set_dynamics_slots)."""
+        self.sched = None if sched is None else np.ascontiguousarray(sched, dtype=np.int32)
         A = _f64(A)
         Bm = _f64(B)
         n, m = A.shape[-1], Bm.shape[-1]
@@ -352,7 +355,7 @@ class Problem:
         mdl = self.model
         if mdl.per_instance:
             model = LinearModel(mdl.A[i0:i1].copy(), mdl.B[i0:i1].copy(), mdl.d[i0:i1].copy(), dt=mdl.dt,
-                                per_instance=True)
+                                per_instance=True, sched=None if mdl.sched is None else mdl.sched[i0:i1].copy())
         else:
             model = LinearModel(mdl.A.copy(), mdl.B.copy(), mdl.d.copy(), dt=mdl.dt, per_instance=False)
         cons = ConstraintList(self.n, self.m, self.N)

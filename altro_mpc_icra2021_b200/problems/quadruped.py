@@ -83,11 +83,31 @@ def sample_batch(batch: int, seed: int = 0xA1720 + 3):
     return t0, x_curr, foot_rel
 
 
-def mpc_problem(batch: int = 1, linearized_friction: bool = True, seed: int = 0xA1720 + 3, N: int = N_HORIZON):
+def gait_slot_model(t0: np.ndarray, foot_rel: np.ndarray, ticks: int, N: int = N_HORIZON, dt: float = DT):
+    """The same LTV models as `linearized_dynamics`, stored once per gait phase: at the benchmark's linearisation point
+    A_k and d_k are constant and B_k depends on the knot only through the contact pattern, i.e. through the gait phase.
+    Returns A, B, d with shape (B, 4, ...) and the schedule sched[b, j] = phase at time t0_b + j*dt (update_dt == dt,
+    MPC.yaml:22,52), for `ticks` control ticks of an N-knot horizon."""
+    Bn = t0.shape[0]
+    contacts = np.broadcast_to(TROT.T[None], (Bn, 4, 4))  # [b, phase, foot]
+    A, Bm, d = linearized_dynamics(contacts, foot_rel, dt)
+    tj = (t0[:, None] + np.arange(ticks + N)[None, :] * dt) % PHASE_T.sum()
+    sched = np.searchsorted(np.cumsum(PHASE_T), tj, side="right").astype(np.int32)
+    return A, Bm, d, sched
+
+
+def mpc_problem(batch: int = 1, linearized_friction: bool = True, seed: int = 0xA1720 + 3, N: int = N_HORIZON,
+                gait_slots: int = 0):
+    """gait_slots = number of control ticks to schedule: the dynamics are then stored per gait phase with a schedule
+    (closed-loop runs on the device); 0 = materialised per-knot A_k, B_k, d_k rebuilt by `advance` every tick."""
     n = m = 12
     t0, x_curr, foot_rel = sample_batch(batch, seed)
-    A, Bm, d = linearized_dynamics(contact_schedule(t0, N), foot_rel)
-    model = LinearModel(A, Bm, d, dt=DT)
+    if gait_slots:
+        A, Bm, d, sched = gait_slot_model(t0, foot_rel, gait_slots, N)
+        model = LinearModel(A, Bm, d, dt=DT, sched=sched)
+    else:
+        A, Bm, d = linearized_dynamics(contact_schedule(t0, N), foot_rel)
+        model = LinearModel(A, Bm, d, dt=DT)
     cons = ConstraintList(n, m, N)
     for i in range(4):
         idx = (CONTROL, np.arange(3 * i, 3 * i + 3))

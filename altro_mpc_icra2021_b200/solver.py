@@ -30,7 +30,7 @@ LIB_PATH = os.path.join(_HERE, "libaltro_b200.so")
 
 ABI_SYMBOLS = [
     "altro_default_options", "altro_create", "altro_destroy", "altro_last_error", "altro_set_stream",
-    "altro_set_options", "altro_set_dynamics", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint",
+    "altro_set_options", "altro_set_dynamics", "altro_set_dynamics_slots", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint",
     "altro_update_constraint_data", "altro_set_x0", "altro_set_trajectory", "altro_get_trajectory", "altro_dual_len",
     "altro_set_duals", "altro_get_duals", "altro_shift_fill", "altro_solve", "altro_sync", "altro_get_stats",
     "altro_get_timing", "altro_get_phase_cycles", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0", "altro_mpc_run",
@@ -179,8 +179,12 @@ class ALTROSolver:
             self._push_options()
         if d["dyn"]:
             mdl = p.model
-            self._ck(self.lib.altro_set_dynamics(self.h, int(mdl.per_knot), int(mdl.per_instance), _p(mdl.A),
-                                                 _p(mdl.B), _p(mdl.d)))
+            if mdl.sched is not None:
+                self._ck(self.lib.altro_set_dynamics_slots(self.h, mdl.A.shape[1], _p(mdl.A), _p(mdl.B), _p(mdl.d),
+                                                           _p(mdl.sched), mdl.sched.shape[1]))
+            else:
+                self._ck(self.lib.altro_set_dynamics(self.h, int(mdl.per_knot), int(mdl.per_instance), _p(mdl.A),
+                                                     _p(mdl.B), _p(mdl.d)))
             d["dyn"] = False
         if d["ref"]:
             self._ck(self.lib.altro_set_reference(self.h, _p(p.Xref), _p(p.Uref)))

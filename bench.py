@@ -67,7 +67,9 @@ class Workload:
             self.opts, self.track, self.noise_model = random_linear.mpc_options(), (Xt, Ut), (1, 0.01, 0.0)
             self.desc = "random_linear_mpc: n=12 m=6 N=21, control bounds, tracking MPC"
         elif name in ("quadruped", "quadruped_soc"):
-            self.prob, self.qstate = quadruped.mpc_problem(batch, linearized_friction=(name == "quadruped"), seed=seed)
+            # configs[2]: dynamics stored once per gait phase + schedule, so the closed-loop run stays on the device
+            self.prob, _ = quadruped.mpc_problem(batch, linearized_friction=(name == "quadruped"), seed=seed,
+                                                 gait_slots=512)
             self.opts, self.noise_model = quadruped.mpc_options(), (0, 1e-3, 0.0)
             self.k = np.zeros(batch, dtype=np.int64)
             self.desc = ("quadruped: n=m=12 N=15, per-instance LTV dynamics, "

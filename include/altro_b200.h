@@ -80,6 +80,13 @@ int altro_set_options(altro_handle_t h, const altro_opts_t *opts);
 int altro_set_dynamics(altro_handle_t h, int per_knot, int per_instance, const double *A, const double *B,
                        const double *d);
 
+/* Gait-scheduled LTV models (quadruped, altro_solver.jl:5-42 + gait.jl:1-9): instead of re-uploading A_k,B_k,d_k at
+ * every control tick, upload per instance the `nslots` distinct models A[B][nslots][n][n].. (one per gait phase) and
+ * the schedule sched[B][sched_len] of slot indices along absolute time: knot k of the MPC step that follows s
+ * transitions uses slot sched[inst][s + k].  altro_mpc_transition / altro_mpc_run advance s. */
+int altro_set_dynamics_slots(altro_handle_t h, int nslots, const double *A, const double *B, const double *d,
+                             const int *sched, int sched_len);
+
 /* LQRObjective / TrackingObjective diagonal weights (mpc.jl:26-29, ALTROParams.jl:46-47,81). */
 int altro_set_cost_diag(altro_handle_t h, const double *Q, const double *R, const double *Qf);
 

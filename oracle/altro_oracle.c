@@ -198,12 +198,20 @@ static double csum(const double *arr, int count)
 
 /* ---------------------------------------------------------------- data access */
 
+/* current MPC step of the instance being solved by this thread (gait-scheduled models only) */
+static _Thread_local int orc_step = 0;
+
 static void dyn_ptrs(const orc_problem_t *pb, int inst, int k, const double **A, const double **Bm,
                      const double **d)
 {
     size_t idx = 0;
-    if (pb->dyn_per_instance) idx = (size_t)inst * (pb->dyn_per_knot ? (size_t)(pb->N - 1) : 1);
-    if (pb->dyn_per_knot) idx += (size_t)k;
+    if (pb->sched) {
+        int s0 = orc_step < pb->sched_len - pb->N ? orc_step : pb->sched_len - pb->N;
+        idx = (size_t)inst * pb->dyn_slots + (size_t)pb->sched[(size_t)inst * pb->sched_len + s0 + k];
+    } else {
+        if (pb->dyn_per_instance) idx = (size_t)inst * (pb->dyn_per_knot ? (size_t)(pb->N - 1) : 1);
+        if (pb->dyn_per_knot) idx += (size_t)k;
+    }
     *A = pb->A + idx * pb->n * pb->n;
     *Bm = pb->Bm + idx * pb->n * pb->m;
     *d = pb->d + idx * pb->n;
@@ -899,6 +907,7 @@ static void *worker(void *arg)
         memcpy(w->U, j->U + (size_t)i * (N - 1) * m, sizeof(double) * (size_t)(N - 1) * m);
         if (j->run) memcpy(w->X, j->X + (size_t)i * N * n, sizeof(double) * (size_t)N * n);
         for (int st = 0; st < steps; ++st) {
+            orc_step = pb->step0 + (j->run ? st + 1 : 0);
             if (j->run) {
                 transition(pb, j->run, w, i, st, l);
                 if (j->x0_log) memcpy(j->x0_log + ((size_t)st * B + i) * n, pb->x0 + (size_t)i * n, sizeof(double) * n);

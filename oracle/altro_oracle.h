@@ -71,6 +71,10 @@ typedef struct {
     double dt;
     int dyn_per_knot, dyn_per_instance; /* A[inst?][knot?][n][n], Bm[..][n][m], d[..][n] */
     const double *A, *Bm, *d;
+    /* optional gait schedule (altro_set_dynamics_slots): A[B][dyn_slots][n][n].., knot k of the solve that follows
+     * `step0` transitions uses slot sched[inst][min(step0, sched_len - N) + k]; sched == NULL disables */
+    int dyn_slots, sched_len, step0;
+    const int *sched;
     const double *Q, *R, *Qf;   /* diagonal weights, shared: [n], [m], [n] */
     const double *xref, *uref;  /* [B][N][n], [B][N-1][m] tracking reference */
     const double *x0;           /* [B][n] */

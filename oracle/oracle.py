@@ -27,6 +27,7 @@ class _Problem(C.Structure):
     _fields_ = [("n", C.c_int), ("m", C.c_int), ("N", C.c_int), ("B", C.c_int), ("dt", C.c_double),
                 ("dyn_per_knot", C.c_int), ("dyn_per_instance", C.c_int),
                 ("A", C.c_void_p), ("Bm", C.c_void_p), ("d", C.c_void_p),
+                ("dyn_slots", C.c_int), ("sched_len", C.c_int), ("step0", C.c_int), ("sched", C.c_void_p),
                 ("Q", C.c_void_p), ("R", C.c_void_p), ("Qf", C.c_void_p),
                 ("xref", C.c_void_p), ("uref", C.c_void_p), ("x0", C.c_void_p),
                 ("ncon", C.c_int), ("con", C.POINTER(_Con))]
@@ -118,6 +119,8 @@ class OracleProblem:
         p.n, p.m, p.N, p.B, p.dt = prob.n, prob.m, prob.N, prob.B, prob.dt
         p.dyn_per_knot, p.dyn_per_instance = int(mdl.per_knot), int(mdl.per_instance)
         p.A, p.Bm, p.d = _ptr(mdl.A), _ptr(mdl.B), _ptr(mdl.d)
+        if getattr(mdl, "sched", None) is not None:
+            p.dyn_slots, p.sched_len, p.step0, p.sched = mdl.A.shape[1], mdl.sched.shape[1], 0, _ptr(mdl.sched)
         p.Q, p.R, p.Qf = _ptr(prob.obj.Q), _ptr(prob.obj.R), _ptr(prob.obj.Qf)
         p.xref, p.uref, p.x0 = _ptr(prob.Xref), _ptr(prob.Uref), _ptr(prob.x0)
         p.ncon = len(cons)
@@ -134,6 +137,7 @@ class OracleProblem:
         it, ito, st, ls = (np.zeros(B, np.int32) for _ in range(4))
         cost, cal, cmax, pmax = (np.zeros(B) for _ in range(4))
         o = _opts_struct(opts)
+        self.c.step0 = getattr(self, "step_abs", 0)
         rc = lib().orc_solve_batch(C.byref(self.c), C.byref(o), i0, i1, nthreads, _ptr(pr.X), _ptr(pr.U),
                                    _ptr(self.lam), _ptr(it), _ptr(ito), _ptr(st), _ptr(ls), _ptr(cost),
                                    _ptr(cal), _ptr(cmax), _ptr(pmax))
@@ -164,6 +168,8 @@ class OracleProblem:
         cost, cmax = np.zeros((steps, B)), np.zeros((steps, B))
         x0l, u0l = np.zeros((steps, B, pr.n)), np.zeros((steps, B, pr.m))
         o = _opts_struct(opts)
+        self.c.step0 = getattr(self, "step_abs", 0)
+        self.step_abs = self.c.step0 + steps
         rc = lib().orc_mpc_run(C.byref(self.c), C.byref(o), C.byref(run), nthreads, _ptr(pr.X), _ptr(pr.U),
                                _ptr(self.lam), _ptr(it), _ptr(ito), _ptr(st), _ptr(ls), _ptr(cost), _ptr(cmax),
                                _ptr(x0l), _ptr(u0l))

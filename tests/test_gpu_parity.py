@@ -307,3 +307,31 @@ def test_closed_loop_run_matches_oracle_and_stepwise_path(family):
     assert np.array_equal(ps.X, pg.X) and np.array_equal(ps.U, pg.U)
     # and the run can be continued: two runs of 2 + 3 steps equal one of 5
     pc = copy.deepcopy(prob)  # prob was advanced by the oracle run; rebuild the starting point instead
+
+
+@pytest.mark.parametrize("linearized", [True, False])
+def test_quadruped_closed_loop_run_with_gait_schedule(linearized):
+    B, steps = 64, 5
+    prob, _ = quadruped.mpc_problem(B, linearized_friction=linearized, seed=41, gait_slots=steps + 2)
+    opts = quadruped.mpc_options()
+    noise = mpc.rng_for(6, 6).standard_normal((steps, B, 12))
+    pg = copy.deepcopy(prob)
+    o, g = OracleSolver(prob, opts, nthreads=8).solve(), gpu_solver(pg, opts).solve()
+    assert_bit_identical(pg, g.stats, g.get_duals(), o.stats, "initial")
+    g.set_noise_model(0, 1e-3, 0.0)
+    g.set_noise_bank(noise)
+    rg = g.mpc_run(steps)
+    ro = o.op.mpc_run(opts, steps, noise, (0, 1e-3, 0.0), None, None, True, nthreads=8)
+    for k in ro:
+        assert np.array_equal(rg[k], ro[k]), k
+    assert np.array_equal(pg.X, prob.X) and np.array_equal(pg.U, prob.U) and np.array_equal(g.get_duals(), o.op.lam)
+    assert np.all(rg["status"] == 1)
+    # one more tick through the per-step API continues the same schedule
+    prob.set_initial_state(prob.X[:, 1, :].copy())
+    o.op.shift_fill(True, True)
+    o.op.step_abs = steps + 1
+    o.solve()
+    g.set_noise_bank(None)
+    g.mpc_transition(None, shift=True)
+    g.solve()
+    assert np.array_equal(pg.X, prob.X) and np.array_equal(g.stats.iterations, o.stats.iterations)

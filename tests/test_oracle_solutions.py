@@ -194,3 +194,29 @@ def test_families_converge_and_are_feasible(family):
         f = r.U.reshape(prob.B, prob.N - 1, 4, 3)
         assert np.all(f[..., 2] >= -1e-4) and np.all(f[..., 2] <= 133 + 1e-4)
         assert np.all(np.abs(f[..., 0]) <= 0.5 * f[..., 2] + 1e-4) and np.all(np.abs(f[..., 1]) <= 0.5 * f[..., 2] + 1e-4)
+
+
+def test_gait_scheduled_dynamics_equal_materialised_models():
+    """Quadruped: dynamics stored once per gait phase + a schedule (closed-loop runs on the device) must give the
+    same bits as the materialised per-knot A_k, B_k, d_k the reference rebuilds every tick (altro_solver.jl:5-42)."""
+    B, steps = 6, 4
+    pq, _ = quadruped.mpc_problem(B, linearized_friction=True, seed=31, gait_slots=steps + 1)
+    pm, _ = quadruped.mpc_problem(B, linearized_friction=True, seed=31)
+    sched = pq.model.sched
+    idx = np.arange(B)[:, None]
+    assert np.array_equal(pq.model.B[idx, sched[:, :pq.N - 1]], pm.model.B)
+    opts = quadruped.mpc_options()
+    oq, om = OracleProblem(pq), OracleProblem(pm)
+    rq, rm = oq.solve(opts), om.solve(opts)
+    assert np.array_equal(rq.X, rm.X) and np.array_equal(rq.iterations, rm.iterations)
+    noise = mpc.rng_for(4, 4).standard_normal((steps, B, 12))
+    run = oq.mpc_run(opts, steps, noise, (0, 1e-3, 0.0), None, None, True, nthreads=2)
+    for st in range(steps):  # the same loop by hand on materialised models
+        pm.set_initial_state(pm.X[:, 1, :] + noise[st] * 1e-3)
+        sl = sched[:, st + 1:st + pq.N]
+        pm.set_dynamics(pq.model.A[idx, sl], pq.model.B[idx, sl], pq.model.d[idx, sl])
+        om.shift_fill(True, True)
+        r = om.solve(opts)
+        assert np.array_equal(r.iterations, run["iterations"][st]) and np.array_equal(pm.X[:, 0], run["x0"][st])
+        assert np.array_equal(pm.U[:, 0], run["u0"][st])
+    assert np.array_equal(pm.X, pq.X) and np.array_equal(pm.U, pq.U)
