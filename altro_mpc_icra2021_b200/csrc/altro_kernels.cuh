@@ -720,95 +720,112 @@ struct Ctx {
                 }
                 gsync<T>();
                 ALTRO_TICK(2);
-                // P3: LDL' of Quu + rho I, kept as the un-normalised lower factor X (L = X diag(r)) and the
-                //     reciprocal pivots r = 1/D, so that there is one division per column and none per entry.
-                //     m <= 32: warp 0 alone, one lane per row, __syncwarp between columns.
+                // P3 + P4: LDL' of Quu + rho I, kept as the un-normalised lower factor X (L = X diag(r)) and the
+                //     reciprocal pivots r = 1/D (one division per column, none per entry), then
+                //     [K | d] = -(Quu + rho I)^-1 [Qux | Qu]: forward y = L^-1 b, z = y r, backward
+                //     x_i = z_i - r_i sum_{q>i} X[q][i] x_q (q descending).  One right-hand side per thread.
                 bool bad = false;
-                if (m <= 32) {
-                    if (warp == 0) {
-                        double rprev = 0.0;  // reciprocal pivot of the previous column (linv[j-1] is still in flight)
-                        for (int j = 0; j < m; ++j) {
-                            if (lane >= j && lane < m) {
-                                double acc = L[lane * m + j];
-                                for (int l = 0; l < j; ++l)
-                                    acc = fma(-L[lane * m + l], L[j * m + l] * (l == j - 1 ? rprev : linv[l]), acc);
-                                L[lane * m + j] = acc;
-                            }
-                            __syncwarp();
-                            const double piv = L[j * m + j];
-                            if (!(piv > 0.0)) { bad = true; break; }
-                            rprev = 1.0 / piv;
-                            if (lane == 0) linv[j] = rprev;
+                double *Kk = K + k * m * n, *dk_ = dv + k * m;
+                if (NU > 0 && NU <= 4) {
+                    // tiny control dimension: every lane factorises in registers (no barrier, no broadcast),
+                    // lanes c <= n then solve their own right-hand side
+                    constexpr int MM = NU > 0 ? NU : 1;
+                    double Xr[MM * MM], rr[MM];
+#pragma unroll
+                    for (int j = 0; j < MM; ++j) {
+#pragma unroll
+                        for (int i = j; i < MM; ++i) {
+                            double acc = L[i * MM + j];
+#pragma unroll
+                            for (int l = 0; l < j; ++l) acc = fma(-Xr[i * MM + l], Xr[j * MM + l] * rr[l], acc);
+                            Xr[i * MM + j] = acc;
                         }
-                        if (lane == 0) bc[5] = bad ? 1.0 : 0.0;
+                        if (!(Xr[j * MM + j] > 0.0)) { bad = true; break; }
+                        rr[j] = __drcp_rn(Xr[j * MM + j]);
                     }
-                    gsync<T>();
-                    bad = bc[5] != 0.0;
+                    if (!bad) {
+                        for (int c = tid; c <= n; c += T) {
+                            double *bp = (c < n) ? Kk + c : dk_;
+                            const double *src = (c < n) ? Qux + c : Qu;
+                            const int st = (c < n) ? n : 1;
+                            double bb[MM];
+#pragma unroll
+                            for (int i = 0; i < MM; ++i) {
+                                double acc = -src[i * st];
+#pragma unroll
+                                for (int l = 0; l < i; ++l) acc = fma(-Xr[i * MM + l], bb[l] * rr[l], acc);
+                                bb[i] = acc;
+                            }
+#pragma unroll
+                            for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
+#pragma unroll
+                            for (int i = MM - 1; i >= 0; --i) {
+                                double acc2 = 0.0;
+#pragma unroll
+                                for (int l = MM - 1; l > i; --l) acc2 = fma(Xr[l * MM + i], bb[l], acc2);
+                                bb[i] = fma(-rr[i], acc2, bb[i]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
+                        }
+                    }
+                    ALTRO_TICK(3);
                 } else {
-                    for (int j = 0; j < m; ++j) {
-                        for (int i = j + tid; i < m; i += T) {
-                            double acc = L[i * m + j];
-                            for (int l = 0; l < j; ++l) acc = fma(-L[i * m + l], L[j * m + l] * linv[l], acc);
-                            L[i * m + j] = acc;
+                    if (m <= 32) {  // warp 0 alone, one lane per row, one __syncwarp per column
+                        if (warp == 0) {
+                            double rprev = 0.0;  // reciprocal pivot of the previous column (linv[j-1] is still in flight)
+                            for (int j = 0; j < m; ++j) {
+                                if (lane >= j && lane < m) {
+                                    double acc = L[lane * m + j];
+                                    for (int l = 0; l < j; ++l)
+                                        acc = fma(-L[lane * m + l], L[j * m + l] * (l == j - 1 ? rprev : linv[l]), acc);
+                                    L[lane * m + j] = acc;
+                                }
+                                __syncwarp();
+                                const double piv = L[j * m + j];
+                                if (!(piv > 0.0)) { bad = true; break; }
+                                rprev = __drcp_rn(piv);
+                                if (lane == 0) linv[j] = rprev;
+                            }
+                            if (lane == 0) bc[5] = bad ? 1.0 : 0.0;
                         }
                         gsync<T>();
-                        const double piv = L[j * m + j];
-                        if (!(piv > 0.0)) { bad = true; break; }  // same value in every thread
-                        if (tid == 0) linv[j] = 1.0 / piv;
-                        gsync<T>();
+                        bad = bc[5] != 0.0;
+                    } else {
+                        for (int j = 0; j < m; ++j) {
+                            for (int i = j + tid; i < m; i += T) {
+                                double acc = L[i * m + j];
+                                for (int l = 0; l < j; ++l) acc = fma(-L[i * m + l], L[j * m + l] * linv[l], acc);
+                                L[i * m + j] = acc;
+                            }
+                            gsync<T>();
+                            const double piv = L[j * m + j];
+                            if (!(piv > 0.0)) { bad = true; break; }  // same value in every thread
+                            if (tid == 0) linv[j] = __drcp_rn(piv);
+                            gsync<T>();
+                        }
+                    }
+                    ALTRO_TICK(3);
+                    if (!bad) {
+                        for (int c = tid; c <= n; c += T) {  // serial substitution per right-hand side, in place
+                            double *bp = (c < n) ? Kk + c : dk_;
+                            const double *src = (c < n) ? Qux + c : Qu;
+                            const int st = (c < n) ? n : 1;
+                            for (int i = 0; i < m; ++i) {
+                                double acc = -src[i * st];
+                                for (int l = 0; l < i; ++l) acc = fma(-L[i * m + l], bp[l * st] * linv[l], acc);
+                                bp[i * st] = acc;
+                            }
+                            for (int i = 0; i < m; ++i) bp[i * st] = bp[i * st] * linv[i];
+                            for (int i = m - 1; i >= 0; --i) {
+                                double acc2 = 0.0;
+                                for (int l = m - 1; l > i; --l) acc2 = fma(L[l * m + i], bp[l * st], acc2);
+                                bp[i * st] = fma(-linv[i], acc2, bp[i * st]);
+                            }
+                        }
                     }
                 }
                 if (bad) { restart = true; break; }
-                ALTRO_TICK(3);
-                // P4: [K | d] = -(Quu + rho I)^-1 [Qux | Qu] by forward / backward substitution, one (row, column)
-                //     entry per thread, all columns advancing together, one barrier per elimination step.
-                //     Forward: y = L^-1 b (consumers rescale y_l by r_l themselves), z = D^-1 y;
-                //     backward: x_i = z_i - r_i sum_{q>i} X[q][i] x_q, the sums accumulated in T1 | t1.
-                double *Kk = K + k * m * n, *dk_ = dv + k * m;
-                const int ntask = m * (n + 1);
-                for (int e = tid; e < ntask; e += T) {  // b = -[Qux | Qu], backward accumulators = 0
-                    const int i = e / (n + 1), c = e - i * (n + 1);
-                    if (c < n) { Kk[i * n + c] = -Qux[i * n + c]; T1[i * n + c] = 0.0; }
-                    else { dk_[i] = -Qu[i]; t1[i] = 0.0; }
-                }
-                gsync<T>();
-                for (int l = 0; l < m - 1; ++l) {
-                    const double rl = linv[l];
-                    for (int e = tid; e < ntask; e += T) {
-                        const int i = e / (n + 1), c = e - i * (n + 1);
-                        if (i > l) {
-                            double *bi = (c < n) ? Kk + i * n + c : dk_ + i;
-                            const double yl = (c < n) ? Kk[l * n + c] : dk_[l];
-                            *bi = fma(-L[i * m + l], yl * rl, *bi);
-                        }
-                    }
-                    gsync<T>();
-                }
-                for (int e = tid; e < ntask; e += T) {  // z = y r
-                    const int i = e / (n + 1), c = e - i * (n + 1);
-                    double *bi = (c < n) ? Kk + i * n + c : dk_ + i;
-                    *bi = *bi * linv[i];
-                }
-                gsync<T>();
-                for (int l = m - 1; l >= 1; --l) {
-                    const double rl = linv[l];
-                    for (int e = tid; e < ntask; e += T) {
-                        const int i = e / (n + 1), c = e - i * (n + 1);
-                        if (i < l) {
-                            const double zl = (c < n) ? Kk[l * n + c] : dk_[l];
-                            const double sl = (c < n) ? T1[l * n + c] : t1[l];
-                            double *ai = (c < n) ? T1 + i * n + c : t1 + i;
-                            *ai = fma(L[l * m + i], fma(-rl, sl, zl), *ai);  // x_l recomputed by every consumer
-                        }
-                    }
-                    gsync<T>();
-                }
-                for (int e = tid; e < ntask; e += T) {  // x_i = z_i - r_i acc_i
-                    const int i = e / (n + 1), c = e - i * (n + 1);
-                    double *bi = (c < n) ? Kk + i * n + c : dk_ + i;
-                    const double acc2 = (c < n) ? T1[i * n + c] : t1[i];
-                    *bi = fma(-linv[i], acc2, *bi);
-                }
                 gsync<T>();
                 ALTRO_TICK(4);
                 // P5: [T1 | t1] = Quu [K | d] + [Qux | Qu]
