@@ -22,7 +22,7 @@ namespace {
 thread_local std::string g_err;
 
 struct HostCon {
-    int sense, side, k0, k1, p, w, per_knot, per_instance, rowsparse;
+    int sense, side, k0, k1, p, w, per_knot, per_instance, rowsparse, track = 0;
     std::vector<int> inds, rs_col;
     std::vector<double> rs_coef;
     double *G_dev = nullptr, *h_dev = nullptr, *rs_coef_dev = nullptr;
@@ -66,6 +66,7 @@ struct altro_handle_s {
     std::vector<HostCon> cons;
     ConDesc *con_dev = nullptr;
     int *itab_dev = nullptr;
+    double *ex_glob = nullptr;
     int P = 0, EX = 0, ITAB = 0;
     bool finalized = false, have_dyn = false, have_cost = false, have_ref = false, have_x0 = false;
     // MPC track
@@ -276,6 +277,7 @@ int finalize(altro_handle_t h)
         dsc.dual_off = P;
         dsc.ex_off = EX;
         dsc.ex_stride = c.rowsparse ? 2 * c.w : c.w + c.w * (c.w + 1) / 2;
+        dsc.track = c.track;
         dsc.tgt_off = TG;
         TG += dsc.ex_stride;
         // gather sources: (block, offset inside the block's per-knot expansion) for every target it touches
@@ -317,7 +319,10 @@ int finalize(altro_handle_t h)
     const int maxdim = std::max(n, m);
     int T = h->threads_req;
     if (const char *e = getenv("ALTRO_B200_THREADS")) T = atoi(e);
-    if (T == 0) T = maxdim <= 8 ? 32 : maxdim <= 16 ? 64 : maxdim <= 32 ? 128 : 256;
+    if (T == 0) {  // measured on B200 (scripts/dev_perf.py sweeps): one warp for tiny blocks, 2-4 warps for 12-dim problems
+        const int work = n * (n + m);
+        T = maxdim <= 8 ? 32 : maxdim <= 16 ? ((work >= 250 || N >= 60) ? 128 : 64) : maxdim <= 32 ? 128 : 256;
+    }
     if (T != 32 && T != 64 && T != 128 && T != 256) return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 32, 64, 128 or 256");
     h->threads = T;
     h->dyn_in_smem = (!h->dyn_per_knot && !h->dyn_per_instance) ? 1 : 0;
@@ -332,6 +337,10 @@ int finalize(altro_handle_t h)
     if (smem > (size_t)prop.sharedMemPerBlockOptin && h->dyn_in_smem) {
         h->dyn_in_smem = 0;
         smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, 0, 0, T, h->ITAB);
+    }
+    if (smem > (size_t)prop.sharedMemPerBlockOptin && EX > 0) {  // long horizons: expansion blocks go to global memory
+        CK(h, dalloc(&h->ex_glob, (size_t)B * EX));
+        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), 0, 0, 0, T, h->ITAB);
     }
     if (smem > (size_t)prop.sharedMemPerBlockOptin) {
         char buf[256];
@@ -461,7 +470,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->x0_snap, h->xref_snap, h->uref_snap, h->kidx_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -640,6 +649,40 @@ int altro_add_constraint(altro_handle_t h, int sense, int side, int k0, int k1, 
     return ALTRO_OK;
 }
 
+int altro_add_track_constraint(altro_handle_t h, int sense, int side, int k0, int k1, int p, int w, const int *inds,
+                               const double *G, const double *hv, int Nt, int *con_id)
+{
+    if (Nt < 1) return fail(h, ALTRO_ERR_INVALID, "empty constraint timeline");
+    // registered as a shared block with Nt "knots" of data, then flagged as a timeline
+    REQ(h);
+    const int kmax = side == ALTRO_CONTROL ? h->N - 1 : h->N;
+    if (k0 < 0 || k1 > kmax || k1 <= k0) return fail(h, ALTRO_ERR_INVALID, "bad knot range (control blocks end at N-1)");
+    int id = -1;
+    // temporarily widen the range so that add_constraint sizes the data as [Nt][p][w]
+    const int saveN = h->N;
+    h->N = Nt + 1 + k0;
+    int rc = altro_add_constraint(h, sense, side, k0, k0 + Nt, p, w, inds, 1, 0, G, hv, &id);
+    h->N = saveN;
+    if (rc) return rc;
+    HostCon &c = h->cons[id];
+    c.k1 = k1;
+    c.per_knot = 0;
+    c.track = Nt;
+    c.rowsparse = 0;
+    if (p > PMAX || w > DENSE_W) return fail(h, ALTRO_ERR_UNSUPPORTED, "dense constraint block larger than 8 rows x 8 indices");
+    if (con_id) *con_id = id;
+    return ALTRO_OK;
+}
+
+int altro_set_track_index(altro_handle_t h, const int *kidx)
+{
+    REQ(h);
+    if (!kidx) return fail(h, ALTRO_ERR_INVALID, "null index array");
+    CK(h, cudaMemcpyAsync(h->kidx, kidx, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return ALTRO_OK;
+}
+
 int altro_update_constraint_data(altro_handle_t h, int id, const double *G, const double *hv)
 {
     REQ(h);
@@ -771,9 +814,11 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
             P.noise = h->noise_bank + (size_t)(h->bank_pos % h->bank_steps) * h->B * h->n;
             h->bank_pos += steps;
         }
-        P.trackX = h->trackX; P.trackU = h->trackU; P.kidx = h->kidx;
+        P.trackX = h->trackX; P.trackU = h->trackU;
         P.x0_log = h->x0_log; P.u0_log = h->u0_log;
     }
+    P.kidx = h->kidx;
+    P.ex_glob = h->ex_glob;
     P.phase = h->phase;
     P.phase_detail = getenv("ALTRO_B200_PHASE_DETAIL") ? 1 : 0;
     void *args[] = {&P};
@@ -783,7 +828,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     CK(h, cudaLaunchKernel(h->kernel, dim3(h->B), dim3(h->threads), args, (size_t)h->smem, h->stream));
     CK(h, cudaEventRecord(h->ev1, h->stream));
     h->step_abs += steps;
-    if (steps > 0 && h->trackX) {
+    if (steps > 0) {
         advance_kidx_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->kidx, h->B, steps);
         CK(h, cudaGetLastError());
     }
@@ -1020,6 +1065,10 @@ int altro_mpc_transition(altro_handle_t h, const double *noise, int shift)
     CK(h, cudaGetLastError());
     h->have_x0 = true;
     h->step_abs += 1;
+    if (!h->trackX) {  // the transition kernel advances kidx only together with the reference window
+        advance_kidx_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->kidx, h->B, 1);
+        CK(h, cudaGetLastError());
+    }
     if (shift) return altro_shift_fill(h, 1, 1);
     return ALTRO_OK;
 }

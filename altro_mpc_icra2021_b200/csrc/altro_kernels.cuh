@@ -33,7 +33,8 @@ struct ConDesc {
     int dual_off;   // offset of the block in the per-instance dual vector
     int ex_off;     // offset of the block in the per-instance expansion scratch
     int ex_stride;  // per-knot stride there: w + w(w+1)/2 (dense, upper triangle) or 2*w (row-sparse)
-    int tgt_off;    // offset of the block's scatter targets in the shared int table (ex_stride entries)
+    int tgt_off;    // (reserved)
+    int track;      // > 0: G, h are a shared timeline [track][p][w]; knot k reads row min(kidx + k, track - 1)
     const double *G, *h;
     const int *rs_col;
     const double *rs_coef;
@@ -64,6 +65,7 @@ struct Params {
     const double *trackX, *trackU;  // reference track [Nt][n], [Nt-1][m], or nullptr
     const int *kidx;                // per-instance track index of the current window start
     double *x0_log, *u0_log;        // [steps][B][n], [steps][B][m]: closed-loop state and applied control
+    double *ex_glob;                // expansion scratch [B][EX] in global memory when it does not fit in shared, or nullptr
     int phase_detail;               // 1: phase[] holds the backward-pass sub-phase split instead
     long long *phase;               // optional [B][8] cycle counters per phase (profiling aid), or nullptr
     const ConDesc *con;
@@ -162,6 +164,7 @@ struct Ctx {
     size_t dyn_base;
     int dyn_k;
     const int *sched;  // this instance's dynamics schedule at the current MPC step, or nullptr
+    int kcur;          // this instance's position on the shared timelines (reference track, track constraints)
 
     __device__ Ctx(const Params &P_, unsigned char *raw) : P(P_)
     {
@@ -189,7 +192,8 @@ struct Ctx {
         dv = q; q += (N - 1) * m;
         lam = q; q += P.P;
         mu = q; q += MAX_CON;
-        ex = q; q += P.EX;
+        if (P.ex_glob) ex = P.ex_glob + (size_t)inst * P.EX;  // long horizons: expansion blocks live in global memory
+        else { ex = q; q += P.EX; }
         S = q; q += n * n;
         SA = q; q += n * n;
         Qxx = q; q += n * n;
@@ -215,6 +219,7 @@ struct Ctx {
         dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_sched ? (size_t)P.dyn_slots : (P.dyn_per_knot ? (size_t)(N - 1) : 1)) : 0;
         dyn_k = P.dyn_per_knot ? 1 : 0;
         sched = nullptr;
+        kcur = P.kidx ? P.kidx[inst] : 0;
         set_step(0);
     }
 
@@ -240,6 +245,7 @@ struct Ctx {
     }
     __device__ __forceinline__ size_t con_idx(const ConDesc &c, int k) const
     {
+        if (c.track) return (size_t)min(kcur + k, c.track - 1);
         size_t idx = c.per_instance ? (size_t)inst * (c.per_knot ? (size_t)(c.k1 - c.k0) : 1) : 0;
         return idx + (c.per_knot ? (size_t)(k - c.k0) : 0);
     }
@@ -1149,6 +1155,7 @@ struct Ctx {
         for (int st = 0; st < steps; ++st) {
             if (P.steps > 0) {
                 set_step(st + 1);  // the window moves one knot forward with every transition
+                kcur = (P.kidx ? P.kidx[inst] : 0) + st + 1;
                 transition(st);
                 if (st > 0) {  // every solve! starts from reset penalties (and duals, if asked)
                     if (P.o.reset_duals)

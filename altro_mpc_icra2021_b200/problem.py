@@ -146,6 +146,7 @@ class FlatConstraint:
     per_knot: bool = False
     per_instance: bool = False
     name: str = ""
+    track: bool = False  # G (Nt,p,w), h (Nt,p): shared timeline; knot k of instance i reads row min(kidx_i + k, Nt-1)
 
     @property
     def p(self) -> int:
@@ -274,6 +275,19 @@ class LinearConstraint(StageConstraint):
         return [(side, idx, self.A, -self.b, self.sense, self.per_knot, self.per_instance)]
 
 
+class TrackConstraint(StageConstraint):
+    """A y - b (=|<=|in SOC) with time-varying data given once along a timeline: A (Nt,p,w), b (Nt,p).  Knot k of an
+    instance whose timeline position is kidx uses row kidx + k -- what grasp_mpc_helpers.jl:26-55 achieves by
+    rewriting cons[i].A / .b / .c in place before every solve."""
+
+    def __init__(self, n, m, A, b, sense, inds=":control"):
+        self.A, self.b, self.sense, self.inds = _f64(A), _f64(b), _sense_code(sense), inds
+
+    def lower(self, n, m):
+        side, idx = _side_inds(n, m, self.inds)
+        return [(side, idx, self.A, -self.b, self.sense, "track", False)]
+
+
 class ConstraintList:
     """TO.ConstraintList(n,m,N) with add_constraint!(cons, con, knots)."""
 
@@ -297,13 +311,15 @@ class ConstraintList:
             kk1 = min(k1, self.N - 1) if side == CONTROL else k1  # u_N is not a decision variable
             if kk1 <= k0:
                 continue
+            track = per_knot == "track"
+            per_knot = False if track else per_knot
             nk_full, nk = k1 - k0, kk1 - k0
             if per_knot and nk != nk_full:  # drop per-knot data of the clipped terminal knot
                 G = G[..., :nk, :, :]
                 h = h[..., :nk, :]
             self.flat.append(
                 FlatConstraint(sense, side, k0, kk1, np.asarray(idx, np.int32), _f64(G), _f64(h), per_knot,
-                               per_instance, name or type(con).__name__)
+                               per_instance, name or type(con).__name__, track)
             )
 
     def __len__(self):
@@ -343,6 +359,7 @@ class Problem:
         self.Uref = _bcast(obj.Uref, (B, N - 1, m))
         self.X = np.zeros((B, N, n)) if X0 is None else _bcast(X0, (B, N, n))
         self.U = np.zeros((B, N - 1, m)) if U0 is None else _bcast(U0, (B, N - 1, m))
+        self.kidx = np.zeros(B, dtype=np.int32)  # position of every instance on the shared timelines
         if model.per_instance:
             assert model.A.shape[0] == B
         self.dirty = {"x0": True, "ref": True, "dyn": True, "traj": True, "con": set(range(len(self.constraints)))}
@@ -364,10 +381,11 @@ class Problem:
             G = c.G[i0:i1].copy() if c.per_instance else c.G.copy()
             h = c.h[i0:i1].copy() if c.per_instance else c.h.copy()
             cons.flat.append(FlatConstraint(c.sense, c.side, c.k0, c.k1, c.inds.copy(), G, h, c.per_knot,
-                                            c.per_instance, c.name))
+                                            c.per_instance, c.name, c.track))
         obj = Objective(self.obj.Q, self.obj.R, self.obj.Qf, self.Xref[i0:i1], self.Uref[i0:i1])
         p = Problem(model, obj, self.N, self.x0[i0:i1], cons, batch=i1 - i0, X0=self.X[i0:i1], U0=self.U[i0:i1])
         p.dt = self.dt
+        p.kidx[...] = self.kidx[i0:i1]
         return p
 
     # --- mutators (TO.set_initial_state!, TO.update_trajectory!, initial_controls!, model.A[i] = ...)

@@ -39,7 +39,9 @@ def gen_tracking_problem(prob: Problem, X_track: np.ndarray, U_track: np.ndarray
             cons.add_constraint(con, (k0, k1), name)
     mdl = prob.model
     model = LinearModel(mdl.A, mdl.B, mdl.d, dt=mdl.dt, per_instance=mdl.per_instance)
-    return Problem(model, obj, N, x0=Xref[:, 0, :], constraints=cons, batch=batch, X0=Xref, U0=Uref)
+    p = Problem(model, obj, N, x0=Xref[:, 0, :], constraints=cons, batch=batch, X0=Xref, U0=Uref)
+    p.kidx[...] = k_start  # position on the shared timelines (track constraints follow it)
+    return p
 
 
 def window_reference(X_track, U_track, k_start, N):
@@ -80,6 +82,9 @@ class MPCLoop:
         p = self.prob
         x0 = self.plant_step()
         self.k += 1
+        p.kidx += 1
+        if hasattr(self.solver, "set_track_index"):
+            self.solver.set_track_index(p.kidx)
         p.set_initial_state(x0)
         if self.X_track is not None:
             p.update_trajectory(*window_reference(self.X_track, self.U_track, self.k, p.N))

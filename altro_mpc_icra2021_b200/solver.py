@@ -30,7 +30,7 @@ LIB_PATH = os.path.join(_HERE, "libaltro_b200.so")
 
 ABI_SYMBOLS = [
     "altro_default_options", "altro_create", "altro_destroy", "altro_last_error", "altro_set_stream",
-    "altro_set_options", "altro_set_dynamics", "altro_set_dynamics_slots", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint",
+    "altro_set_options", "altro_set_dynamics", "altro_set_dynamics_slots", "altro_set_cost_diag", "altro_set_reference", "altro_add_constraint", "altro_add_track_constraint", "altro_set_track_index",
     "altro_update_constraint_data", "altro_set_x0", "altro_set_trajectory", "altro_get_trajectory", "altro_dual_len",
     "altro_set_duals", "altro_get_duals", "altro_shift_fill", "altro_solve", "altro_sync", "altro_get_stats",
     "altro_get_timing", "altro_get_phase_cycles", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0", "altro_mpc_run",
@@ -126,10 +126,16 @@ class ALTROSolver:
         for c in prob.constraints.flat:
             cid = C.c_int()
             inds = np.ascontiguousarray(c.inds, dtype=np.int32)
-            self._ck(self.lib.altro_add_constraint(self.h, c.sense, c.side, c.k0, c.k1, c.p, c.w, _p(inds),
-                                                   int(c.per_knot), int(c.per_instance), _p(c.G), _p(c.h),
-                                                   C.byref(cid)))
+            if c.track:
+                self._ck(self.lib.altro_add_track_constraint(self.h, c.sense, c.side, c.k0, c.k1, c.p, c.w, _p(inds),
+                                                             _p(c.G), _p(c.h), c.G.shape[0], C.byref(cid)))
+            else:
+                self._ck(self.lib.altro_add_constraint(self.h, c.sense, c.side, c.k0, c.k1, c.p, c.w, _p(inds),
+                                                       int(c.per_knot), int(c.per_instance), _p(c.G), _p(c.h),
+                                                       C.byref(cid)))
         prob.dirty["con"] = set()
+        if any(c.track for c in prob.constraints.flat):
+            self.set_track_index(prob.kidx)
         self.P = prob.constraints.dual_len()
         if pin:
             for a in (prob.x0, prob.Xref, prob.Uref, prob.X, prob.U, prob.model.A, prob.model.B, prob.model.d):
@@ -228,9 +234,11 @@ class ALTROSolver:
     def snapshot(self) -> None:
         self.upload()
         self._ck(self.lib.altro_snapshot(self.h))
+        self._kidx_snap = self.prob.kidx.copy()
 
     def restore(self) -> None:
         self._ck(self.lib.altro_restore(self.h))
+        self.prob.kidx[...] = self._kidx_snap
 
     def sync(self) -> None:
         self._ck(self.lib.altro_sync(self.h))
@@ -264,6 +272,11 @@ class ALTROSolver:
             if p.N > 2:
                 p.U[:, :-1] = p.U[:, 1:].copy()
 
+    def set_track_index(self, kidx) -> None:
+        """Position of every instance on the shared timelines (track constraints, reference track)."""
+        ki = np.ascontiguousarray(kidx, dtype=np.int32)
+        self._ck(self.lib.altro_set_track_index(self.h, _p(ki)))
+
     def set_track(self, X_track, U_track, k_start) -> None:
         Xt = np.ascontiguousarray(X_track, dtype=np.float64)
         Ut = np.ascontiguousarray(U_track, dtype=np.float64)
@@ -294,12 +307,14 @@ class ALTROSolver:
         self.upload()
         nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
         self._ck(self.lib.altro_mpc_transition(self.h, _p(nz), int(shift)))
+        self.prob.kidx += 1
 
     def mpc_run(self, steps: int, shift: bool = True, fetch: bool = True):
         """Closed-loop MPC run on the device: `steps` x {transition; solve!} per instance in one launch.
         Returns a dict of per-step results (see altro_mpc_run) when fetch=True."""
         self.upload()
         self._ck(self.lib.altro_mpc_run(self.h, int(steps), int(shift)))
+        self.prob.kidx += int(steps)  # host mirror of the timeline positions the device just advanced
         self._results_stale = True
         return self.run_results(steps) if fetch else None
 

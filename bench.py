@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from altro_mpc_icra2021_b200.problems import flexsat, mpc, quadruped, random_linear, rocket  # noqa: E402
+from altro_mpc_icra2021_b200.problems import flexsat, grasp, mpc, quadruped, random_linear, rocket  # noqa: E402
 
 METRIC = "batched MPC solves/sec (whole box, device-timed)"
 UNIT = "solves/s"
@@ -62,6 +62,16 @@ class Workload:
             self.prob, self.k = rocket.mpc_problem(cold, Xt, Ut, 21, batch=batch, seed=seed)
             self.opts, self.track, self.noise_model = rocket.mpc_options(), (Xt, Ut), (2, 1e-3, 1e-2)
             self.desc = "rocket_landing: n=6 m=3 N=21, thrust-norm + thrust-angle + glideslope SOC, tracking MPC"
+        elif name == "grasp":
+            # configs[3]: two-finger grasp, per-knot equality + inequality + 2 SOC, data along shared timelines
+            cold = grasp.cold_problem()
+            cs = make_solver(cold, grasp.cold_options())
+            cs.solve()
+            assert cs.stats.status[0] == 1, "cold solve failed"
+            Xt, Ut = cold.X[0].copy(), cold.U[0].copy()
+            self.prob, self.k = grasp.mpc_problem(cold, Xt, Ut, 21, batch=batch, seed=seed)
+            self.opts, self.track, self.noise_model = grasp.mpc_options(), (Xt, Ut), (1, 0.01, 0.0)
+            self.desc = "grasp_optimization: n=m=6 N=21, torque-balance eq + max-force ineq + 2 friction SOC, tracking MPC"
         elif name == "random_linear":
             self.prob, Xt, Ut, self.k = random_linear.mpc_problem(12, 6, 21, batch=batch, seed=seed)
             self.opts, self.track, self.noise_model = random_linear.mpc_options(), (Xt, Ut), (1, 0.01, 0.0)
@@ -100,6 +110,7 @@ class Workload:
 
     def host_advance(self, prob, solver, z):
         """The reference's between-solve update done by the caller on HOST buffers (e2e and CPU arms)."""
+        prob.kidx += 1
         if self.qstate is not None:  # quadruped control tick: new contact schedule -> new B_k, plant step + noise
             quadruped.advance(prob, self.qstate, self.rng)
             solver.shift_fill(True, True)

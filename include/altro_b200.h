@@ -101,6 +101,14 @@ int altro_set_reference(altro_handle_t h, const double *Xref, const double *Uref
 int altro_add_constraint(altro_handle_t h, int sense, int side, int k0, int k1, int p, int w, const int *inds,
                          int per_knot, int per_instance, const double *G, const double *hvec, int *con_id);
 
+/* Time-varying constraint data along a shared timeline (the grasp benchmark's torque-balance / grasp-force /
+ * friction-cone data, rewritten every MPC step by grasp_mpc_helpers.jl:26-55): G[Nt][p][w], h[Nt][p]; knot k of an
+ * instance whose timeline position is kidx reads row min(kidx + k, Nt - 1).  kidx is the per-instance index that
+ * altro_set_track / altro_set_track_index set and altro_mpc_transition / altro_mpc_run advance. */
+int altro_add_track_constraint(altro_handle_t h, int sense, int side, int k0, int k1, int p, int w, const int *inds,
+                               const double *G, const double *hvec, int Nt, int *con_id);
+int altro_set_track_index(altro_handle_t h, const int *kidx);
+
 /* In-place constraint data update cons[1].A[i] = ... (grasp_mpc_helpers.jl:46-55). */
 int altro_update_constraint_data(altro_handle_t h, int con_id, const double *G, const double *hvec);
 

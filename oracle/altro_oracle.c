@@ -143,7 +143,7 @@ static ws_t *ws_new(const orc_problem_t *pb)
         w->ex_off[c] = EX;
         w->rs_base[c] = rows;
         /* row-sparse blocks (bounds): shared data, not a cone, every row has at most one nonzero */
-        int rs = !cc->per_knot && !cc->per_instance && cc->sense != ORC_SOC;
+        int rs = !cc->per_knot && !cc->per_instance && !cc->track && cc->sense != ORC_SOC;
         for (int r = 0; r < cc->p && rs; ++r) {
             int nz = 0;
             for (int j = 0; j < cc->w; ++j)
@@ -217,9 +217,19 @@ static void dyn_ptrs(const orc_problem_t *pb, int inst, int k, const double **A,
     *d = pb->d + idx * pb->n;
 }
 
+/* position of the instance being solved by this thread on the shared timelines */
+static _Thread_local int orc_kcur = 0;
+
 static void con_ptrs(const orc_con_t *c, int inst, int k, const double **G, const double **h)
 {
     size_t idx = 0;
+    if (c->track) {
+        int r = orc_kcur + k;
+        idx = (size_t)(r < c->track - 1 ? r : c->track - 1);
+        *G = c->G + idx * c->p * c->w;
+        *h = c->h + idx * c->p;
+        return;
+    }
     if (c->per_instance) idx = (size_t)inst * (c->per_knot ? (size_t)(c->k1 - c->k0) : 1);
     if (c->per_knot) idx += (size_t)(k - c->k0);
     *G = c->G + idx * c->p * c->w;
@@ -908,6 +918,10 @@ static void *worker(void *arg)
         if (j->run) memcpy(w->X, j->X + (size_t)i * N * n, sizeof(double) * (size_t)N * n);
         for (int st = 0; st < steps; ++st) {
             orc_step = pb->step0 + (j->run ? st + 1 : 0);
+            {
+                const int *ki = j->run && j->run->kidx ? j->run->kidx : pb->kidx;
+                orc_kcur = (ki ? ki[i] : 0) + (j->run ? st + 1 : 0);
+            }
             if (j->run) {
                 transition(pb, j->run, w, i, st, l);
                 if (j->x0_log) memcpy(j->x0_log + ((size_t)st * B + i) * n, pb->x0 + (size_t)i * n, sizeof(double) * n);
@@ -991,6 +1005,7 @@ void orc_evaluate(const orc_problem_t *pb, const orc_opts_t *o, const double *X,
 {
     ws_t *w = ws_new(pb);
     for (int i = 0; i < pb->B; ++i) {
+        orc_kcur = pb->kidx ? pb->kidx[i] : 0;
         const double *x = X + (size_t)i * pb->N * pb->n, *u = U + (size_t)i * (pb->N - 1) * pb->m;
         if (cost) cost[i] = objective_cost(pb, w, i, x, u);
         if (cmax) cmax[i] = max_violation(pb, o, i, x, u);

@@ -62,6 +62,7 @@ typedef struct {
     int p, w;
     int inds[ORC_MAX_W];
     int per_knot, per_instance; /* data layout: G[inst?][knot-k0?][p][w], h[inst?][knot-k0?][p] */
+    int track;                  /* > 0: G, h are a shared timeline [track][p][w]; knot k reads row min(kidx+k, track-1) */
     const double *G;
     const double *h;
 } orc_con_t;
@@ -75,6 +76,7 @@ typedef struct {
      * `step0` transitions uses slot sched[inst][min(step0, sched_len - N) + k]; sched == NULL disables */
     int dyn_slots, sched_len, step0;
     const int *sched;
+    const int *kidx;            /* [B] current position of every instance on the shared timelines, or NULL (= 0) */
     const double *Q, *R, *Qf;   /* diagonal weights, shared: [n], [m], [n] */
     const double *xref, *uref;  /* [B][N][n], [B][N-1][m] tracking reference */
     const double *x0;           /* [B][n] */

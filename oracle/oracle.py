@@ -20,7 +20,7 @@ ORC_MAX_W = 64
 class _Con(C.Structure):
     _fields_ = [("sense", C.c_int), ("side", C.c_int), ("k0", C.c_int), ("k1", C.c_int), ("p", C.c_int),
                 ("w", C.c_int), ("inds", C.c_int * ORC_MAX_W), ("per_knot", C.c_int), ("per_instance", C.c_int),
-                ("G", C.c_void_p), ("h", C.c_void_p)]
+                ("track", C.c_int), ("G", C.c_void_p), ("h", C.c_void_p)]
 
 
 class _Problem(C.Structure):
@@ -28,6 +28,7 @@ class _Problem(C.Structure):
                 ("dyn_per_knot", C.c_int), ("dyn_per_instance", C.c_int),
                 ("A", C.c_void_p), ("Bm", C.c_void_p), ("d", C.c_void_p),
                 ("dyn_slots", C.c_int), ("sched_len", C.c_int), ("step0", C.c_int), ("sched", C.c_void_p),
+                ("kidx", C.c_void_p),
                 ("Q", C.c_void_p), ("R", C.c_void_p), ("Qf", C.c_void_p),
                 ("xref", C.c_void_p), ("uref", C.c_void_p), ("x0", C.c_void_p),
                 ("ncon", C.c_int), ("con", C.POINTER(_Con))]
@@ -113,6 +114,7 @@ class OracleProblem:
             for j, v in enumerate(c.inds):
                 s.inds[j] = int(v)
             s.per_knot, s.per_instance = int(c.per_knot), int(c.per_instance)
+            s.track = c.G.shape[0] if getattr(c, "track", False) else 0
             s.G, s.h = _ptr(c.G), _ptr(c.h)  # live views: in-place constraint-data updates are seen
         mdl = prob.model
         p = _Problem()
@@ -123,6 +125,7 @@ class OracleProblem:
             p.dyn_slots, p.sched_len, p.step0, p.sched = mdl.A.shape[1], mdl.sched.shape[1], 0, _ptr(mdl.sched)
         p.Q, p.R, p.Qf = _ptr(prob.obj.Q), _ptr(prob.obj.R), _ptr(prob.obj.Qf)
         p.xref, p.uref, p.x0 = _ptr(prob.Xref), _ptr(prob.Uref), _ptr(prob.x0)
+        p.kidx = _ptr(prob.kidx)  # live view: the host loop advances prob.kidx in place
         p.ncon = len(cons)
         p.con = C.cast(self.cons, C.POINTER(_Con))
         self.c = p
@@ -158,12 +161,14 @@ class OracleProblem:
             assert nz.shape == (steps, B, pr.n)
             keep.append(nz)
             run.noise = _ptr(nz)
+        ki = np.ascontiguousarray(pr.kidx if kidx is None else kidx, dtype=np.int32).copy()
+        keep.append(ki)
+        run.kidx = _ptr(ki)
         if track is not None:
             Xt = np.ascontiguousarray(track[0], dtype=np.float64)
             Ut = np.ascontiguousarray(track[1], dtype=np.float64)
-            ki = np.ascontiguousarray(kidx, dtype=np.int32)
-            keep += [Xt, Ut, ki]
-            run.trackX, run.trackU, run.kidx, run.Nt = _ptr(Xt), _ptr(Ut), _ptr(ki), Xt.shape[0]
+            keep += [Xt, Ut]
+            run.trackX, run.trackU, run.Nt = _ptr(Xt), _ptr(Ut), Xt.shape[0]
         it, ito, st, ls = (np.zeros((steps, B), np.int32) for _ in range(4))
         cost, cmax = np.zeros((steps, B)), np.zeros((steps, B))
         x0l, u0l = np.zeros((steps, B, pr.n)), np.zeros((steps, B, pr.m))
@@ -175,6 +180,7 @@ class OracleProblem:
                                _ptr(x0l), _ptr(u0l))
         if rc != 0:
             raise RuntimeError(f"orc_mpc_run failed: {rc}")
+        pr.kidx[...] = ki + steps
         return {"iterations": it, "iterations_outer": ito, "status": st, "ls_trials": ls, "cost": cost, "c_max": cmax,
                 "x0": x0l, "u0": u0l}
 

@@ -26,6 +26,9 @@ class OracleSolver:
     def get_duals(self):
         return self.op.lam.copy()
 
+    def set_track_index(self, kidx):
+        pass  # the oracle reads prob.kidx in place
+
 
 def random_lti(n, m, rng, stable=0.95):
     A = rng.standard_normal((n, n))

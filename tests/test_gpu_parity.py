@@ -335,3 +335,34 @@ def test_quadruped_closed_loop_run_with_gait_schedule(linearized):
     g.mpc_transition(None, shift=True)
     g.solve()
     assert np.array_equal(pg.X, prob.X) and np.array_equal(g.stats.iterations, o.stats.iterations)
+
+
+def test_grasp_cold_solve_and_closed_loop_run():
+    """Grasp family: cold solve N=251 (expansion blocks spill to global memory), then a closed-loop MPC run whose
+    constraint data follow each instance along shared timelines."""
+    from altro_mpc_icra2021_b200.problems import grasp
+
+    cold = grasp.cold_problem()
+    cg = copy.deepcopy(cold)
+    oc = OracleSolver(cold, grasp.cold_options(), nthreads=1).solve()
+    gc = gpu_solver(cg, grasp.cold_options()).solve()
+    assert_bit_identical(cg, gc.stats, gc.get_duals(), oc.stats, "cold")
+    assert gc.stats.status[0] == 1
+    Xt, Ut = cold.X[0].copy(), cold.U[0].copy()
+    B, steps = 48, 4
+    prob, ks = grasp.mpc_problem(cold, Xt, Ut, 21, batch=B, seed=8)
+    pg = copy.deepcopy(prob)
+    opts = grasp.mpc_options()
+    o, g = OracleSolver(prob, opts, nthreads=8).solve(), gpu_solver(pg, opts)
+    g.set_track(Xt, Ut, ks)
+    g.solve()
+    assert_bit_identical(pg, g.stats, g.get_duals(), o.stats, "first MPC solve")
+    noise = mpc.rng_for(9, 9).standard_normal((steps, B, 6))
+    g.set_noise_model(1, 0.01, 0.0)
+    g.set_noise_bank(noise)
+    rg = g.mpc_run(steps)
+    ro = o.op.mpc_run(opts, steps, noise, (1, 0.01, 0.0), (Xt, Ut), None, True, nthreads=8)
+    for k in ro:
+        assert np.array_equal(rg[k], ro[k]), k
+    assert np.array_equal(pg.X, prob.X) and np.array_equal(g.get_duals(), o.op.lam) and np.all(rg["status"] == 1)
+    assert np.array_equal(pg.kidx, prob.kidx) and np.array_equal(pg.kidx, ks + steps)

@@ -220,3 +220,43 @@ def test_gait_scheduled_dynamics_equal_materialised_models():
         assert np.array_equal(r.iterations, run["iterations"][st]) and np.array_equal(pm.X[:, 0], run["x0"][st])
         assert np.array_equal(pm.U[:, 0], run["u0"][st])
     assert np.array_equal(pm.X, pq.X) and np.array_equal(pm.U, pq.U)
+
+
+def test_grasp_builder_and_track_constraints_equal_materialised_windows():
+    """Grasp: known-answer dynamics, and constraint data read from shared timelines must equal the
+    per-knot / per-instance windows the reference rewrites before every solve (grasp_mpc_helpers.jl:26-55)."""
+    from altro_mpc_icra2021_b200.problem import ConstraintList, LinearConstraint, Problem
+    from altro_mpc_icra2021_b200.problems import grasp
+
+    cold = grasp.cold_problem()
+    assert np.allclose(cold.model.B[:3, :3], 0.00144 * np.eye(3)) and np.allclose(cold.model.B[3:, 3:], 0.12 * np.eye(3))
+    assert np.allclose(cold.model.d, [0, 0, -0.00282528, 0, 0, -0.23544])
+    rc = OracleProblem(cold).solve(grasp.cold_options())
+    assert rc.status[0] == 1 and np.abs(rc.X[0, -1]).max() < 1e-6
+    B, Nm, steps = 5, 11, 3
+    pt, ks = grasp.mpc_problem(cold, rc.X[0], rc.U[0], Nm, batch=B, seed=3)
+    # the same problem with the windows materialised per knot and per instance
+    cons = ConstraintList(6, 6, Nm)
+    for c in pt.constraints.flat:
+        rows = ks[:, None] + np.arange(c.k1 - c.k0)[None, :]
+        cons.add_constraint(LinearConstraint(6, 6, c.G[rows], -c.h[rows], c.sense, (c.side, c.inds), per_knot=True,
+                                             per_instance=True), (c.k0, c.k1), c.name)
+    pw = Problem(pt.model, pt.obj, Nm, pt.x0, cons, batch=B, X0=pt.X, U0=pt.U)
+    pw.Xref[...], pw.Uref[...] = pt.Xref, pt.Uref
+    opts = grasp.mpc_options()
+    ot, ow = OracleProblem(pt), OracleProblem(pw)
+    for st in range(steps):
+        a, b = ot.solve(opts), ow.solve(opts)
+        assert np.array_equal(a.X, b.X) and np.array_equal(a.lam, b.lam) and np.array_equal(a.iterations, b.iterations)
+        assert np.all(a.status == 1)
+        x0 = pt.X[:, 1, :] * 1.001
+        ks = ks + 1
+        Xr, Ur = mpc.window_reference(rc.X[0], rc.U[0], ks, Nm)
+        for p_, o_ in ((pt, ot), (pw, ow)):
+            p_.set_initial_state(x0)
+            p_.update_trajectory(Xr, Ur)
+            o_.shift_fill(True, True)
+        pt.kidx += 1
+        for ci, c in enumerate(pt.constraints.flat):
+            rows = np.minimum(ks[:, None] + np.arange(c.k1 - c.k0)[None, :], c.G.shape[0] - 1)
+            pw.set_constraint_data(ci, G=c.G[rows], h=c.h[rows])
