@@ -319,10 +319,9 @@ int finalize(altro_handle_t h)
     const int maxdim = std::max(n, m);
     int T = h->threads_req;
     if (const char *e = getenv("ALTRO_B200_THREADS")) T = atoi(e);
-    if (T == 0) {  // measured on B200 (scripts/dev_perf.py sweeps): one warp for tiny blocks, 2-4 warps for 12-dim problems
-        const int work = n * (n + m);
-        T = maxdim <= 8 ? 32 : maxdim <= 16 ? ((work >= 250 || N >= 60) ? 128 : 64) : maxdim <= 32 ? 128 : 256;
-    }
+    if (T == 0)  // measured on B200 (scripts/dev_perf.py sweeps): one warp for tiny blocks, 2 warps for 12-dimensional
+                 // problems, 4 when the horizon is long (flexible satellite), more for the big run-time sized ones
+        T = maxdim <= 8 ? 32 : maxdim <= 16 ? (N >= 60 ? 128 : 64) : maxdim <= 32 ? 128 : 256;
     if (T != 32 && T != 64 && T != 128 && T != 256) return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 32, 64, 128 or 256");
     h->threads = T;
     h->dyn_in_smem = (!h->dyn_per_knot && !h->dyn_per_instance) ? 1 : 0;

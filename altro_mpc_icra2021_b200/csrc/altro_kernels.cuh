@@ -147,6 +147,73 @@ __device__ __forceinline__ double gmax(double v, double *red)
     return s;
 }
 
+// LDL' of the m x m matrix in L (un-normalised lower factor X, reciprocal pivots r) and
+// [K | d] = -(L D L')^-1 [Qux | Qu] for a medium control dimension (quadruped m = 12, random linear m = 6), kept
+// out of line so that its register arrays get a register allocation of their own.  Lane i of warp 0 keeps row i
+// of the factor in registers and fetches the pivot row with shuffles (no shared-memory round trip per column);
+// the factor then goes to shared memory once and every right-hand side is substituted in registers by one thread.
+// Same fma / multiply sequence as the oracle's scalar loops.  Returns true if a pivot is not positive.
+template <int MM, int T>
+__device__ __noinline__ bool ldl_solve_medium(double *L, double *linv, double *flag, const double *Qux, const double *Qu,
+                                              double *Kk, double *dk_, int n)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    bool bad = false;
+    if (warp == 0) {
+        double row[MM], rr[MM];
+        const int li = lane < MM ? lane : MM - 1;
+#pragma unroll
+        for (int j = 0; j < MM; ++j) row[j] = L[li * MM + j];
+#pragma unroll
+        for (int j = 0; j < MM; ++j) {
+            double acc = row[j];
+#pragma unroll
+            for (int l = 0; l < j; ++l) acc = fma(-row[l], __shfl_sync(0xffffffffu, row[l], j) * rr[l], acc);
+            row[j] = acc;
+            const double piv = __shfl_sync(0xffffffffu, acc, j);
+            if (!(piv > 0.0)) { bad = true; break; }
+            rr[j] = __drcp_rn(piv);
+        }
+        if (!bad && lane < MM) {
+#pragma unroll
+            for (int j = 0; j < MM; ++j) L[lane * MM + j] = row[j];
+        }
+        if (!bad && lane == 0) {
+#pragma unroll
+            for (int j = 0; j < MM; ++j) linv[j] = rr[j];
+        }
+        if (lane == 0) *flag = bad ? 1.0 : 0.0;
+    }
+    gsync<T>();
+    bad = *flag != 0.0;
+    if (bad) return true;
+    for (int c = tid; c <= n; c += T) {
+        double *bp = (c < n) ? Kk + c : dk_;
+        const double *src = (c < n) ? Qux + c : Qu;
+        const int st = (c < n) ? n : 1;
+        double bb[MM];
+#pragma unroll
+        for (int i = 0; i < MM; ++i) {
+            double acc = -src[i * st];
+#pragma unroll
+            for (int l = 0; l < i; ++l) acc = fma(-L[i * MM + l], bb[l] * linv[l], acc);
+            bb[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < MM; ++i) bb[i] = bb[i] * linv[i];
+#pragma unroll
+        for (int i = MM - 1; i >= 0; --i) {
+            double acc2 = 0.0;
+#pragma unroll
+            for (int l = MM - 1; l > i; --l) acc2 = fma(L[l * MM + i], bb[l], acc2);
+            bb[i] = fma(-linv[i], acc2, bb[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
+    }
+    return false;
+}
+
 // Per-instance context: shared-memory pointers and problem view.
 template <int NX, int NU, int T>
 struct Ctx {
@@ -776,6 +843,9 @@ struct Ctx {
                         }
                     }
                     ALTRO_TICK(3);
+                } else if (NU > 4 && NU <= 16) {
+                    bad = ldl_solve_medium<(NU > 4 && NU <= 16) ? NU : 5, T>(L, linv, bc + 5, Qux, Qu, Kk, dk_, n);
+                    ALTRO_TICK(3);
                 } else {
                     if (m <= 32) {  // warp 0 alone, one lane per row, one __syncwarp per column
                         if (warp == 0) {
@@ -1181,7 +1251,12 @@ struct Ctx {
 };
 
 template <int NX, int NU, int T>
-__global__ void __launch_bounds__(T, 512 / T) altro_solve_kernel(const __grid_constant__ Params P)
+// Registers: tiny problems (rocket, grasp) are capped at 128 so that 16 warps fit an SM; 12-dimensional and run-time
+// sized problems are shared-memory-limited to a few CTAs per SM anyway and get the full register file (no spills).
+// (measured, scripts/dev_perf.py): quadruped (12,12) is fastest with the whole register file at 4 CTAs/SM; the other
+// 12-dimensional and run-time sized problems with a 168-register cap (6 CTAs/SM at T = 64).
+__global__ void __launch_bounds__(T, ((NX == 12 && NU == 12) ? (256 / T > 0 ? 256 / T : 1)
+                                      : (NX >= 12 || NX == 0) ? (384 / T > 0 ? 384 / T : 1) : 512 / T)) altro_solve_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<NX, NU, T> ctx(P, smem_raw);
