@@ -77,6 +77,7 @@ struct altro_handle_s {
     // launch
     int threads_req = 0, threads = 0, smem = 0, regs = 0, ctas_per_sm = 0, num_sms = 0, dyn_in_smem = 0, ref_in_smem = 1;
     const void *kernel = nullptr;
+    Layout lay;
 };
 
 namespace {
@@ -328,24 +329,22 @@ int finalize(altro_handle_t h)
     // the reference window lives in shared memory unless a track is registered (closed-loop runs read the
     // window straight from the shared, L2-resident track) or the horizon is too long
     h->ref_in_smem = h->trackX ? 0 : 1;
-    size_t smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, h->ref_in_smem, T, h->ITAB);
-    if (smem > (size_t)prop.sharedMemPerBlockOptin && h->ref_in_smem) {  // long horizons: keep the reference in global memory
+    const int ncons = (int)h->cons.size();
+    const size_t limit = (size_t)prop.sharedMemPerBlockOptin;
+    h->lay = make_layout(n, m, N, P, ncons, EX, h->ref_in_smem, h->ITAB);
+    if ((size_t)h->lay.bytes > limit && h->ref_in_smem) {  // long horizons: keep the reference in global memory
         h->ref_in_smem = 0;
-        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, h->dyn_in_smem, 0, T, h->ITAB);
+        h->lay = make_layout(n, m, N, P, ncons, EX, 0, h->ITAB);
     }
-    if (smem > (size_t)prop.sharedMemPerBlockOptin && h->dyn_in_smem) {
-        h->dyn_in_smem = 0;
-        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), EX, 0, 0, T, h->ITAB);
-    }
-    if (smem > (size_t)prop.sharedMemPerBlockOptin && EX > 0) {  // long horizons: expansion blocks go to global memory
+    if ((size_t)h->lay.bytes > limit && EX > 0) {  // longer still: expansion blocks go to global memory
         CK(h, dalloc(&h->ex_glob, (size_t)B * EX));
-        smem = smem_bytes(n, m, N, P, (int)h->cons.size(), 0, 0, 0, T, h->ITAB);
+        h->lay = make_layout(n, m, N, P, ncons, 0, h->ref_in_smem, h->ITAB);
     }
-    if (smem > (size_t)prop.sharedMemPerBlockOptin) {
+    size_t smem = (size_t)h->lay.bytes;
+    if (smem > limit) {
         char buf[256];
         snprintf(buf, sizeof buf, "problem needs %zu B of shared memory per instance, device offers %zu B "
-                 "(n=%d m=%d N=%d P=%d): not supported by the shared-memory-resident kernel", smem,
-                 (size_t)prop.sharedMemPerBlockOptin, n, m, N, P);
+                 "(n=%d m=%d N=%d P=%d): not supported by the shared-memory-resident kernel", smem, limit, n, m, N, P);
         return fail(h, ALTRO_ERR_UNSUPPORTED, buf);
     }
     h->smem = (int)smem;
@@ -802,6 +801,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     P.trace_rows = h->trace_rows;
     P.con = h->con_dev;
     P.itab = h->itab_dev;
+    P.lay = h->lay;
     P.o = h->opts;
     P.dyn_slots = h->dyn_slots; P.sched_len = h->sched_len; P.step0 = h->step_abs; P.dyn_sched = h->sched;
     P.steps = steps; P.shift = shift; P.noise_mode = h->noise_mode; P.Nt = h->Nt;
