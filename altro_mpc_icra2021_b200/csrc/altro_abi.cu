@@ -326,19 +326,25 @@ int finalize(altro_handle_t h)
     if (T != 32 && T != 64 && T != 128 && T != 256) return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 32, 64, 128 or 256");
     h->threads = T;
     h->dyn_in_smem = (!h->dyn_per_knot && !h->dyn_per_instance) ? 1 : 0;
-    // the reference window lives in shared memory unless a track is registered (closed-loop runs read the
-    // window straight from the shared, L2-resident track) or the horizon is too long
-    h->ref_in_smem = h->trackX ? 0 : 1;
     const int ncons = (int)h->cons.size();
     const size_t limit = (size_t)prop.sharedMemPerBlockOptin;
-    h->lay = make_layout(n, m, N, P, ncons, EX, h->ref_in_smem, h->ITAB);
-    if ((size_t)h->lay.bytes > limit && h->ref_in_smem) {  // long horizons: keep the reference in global memory
-        h->ref_in_smem = 0;
-        h->lay = make_layout(n, m, N, P, ncons, EX, 0, h->ITAB);
-    }
-    if ((size_t)h->lay.bytes > limit && EX > 0) {  // longer still: expansion blocks go to global memory
-        CK(h, dalloc(&h->ex_glob, (size_t)B * EX));
-        h->lay = make_layout(n, m, N, P, ncons, 0, h->ref_in_smem, h->ITAB);
+    // Fixed-dimension kernels keep everything (reference window, expansion blocks) in shared memory.  Problems that
+    // do not fit run on the run-time sized kernel, which can leave the reference window in global memory (long
+    // horizons; closed-loop runs then read it straight from the L2-resident track) and, longer still, the
+    // expansion blocks too.
+    h->kernel = find_kernel(n, m, T);
+    h->ref_in_smem = 1;
+    h->lay = make_layout(n, m, N, P, ncons, EX, 1, h->ITAB);
+    if ((size_t)h->lay.bytes > limit || !ALTRO_FIXED_ALL_SMEM) {
+        if ((size_t)h->lay.bytes > limit) h->kernel = kernel_0_0(T);
+        if (h->trackX || (size_t)h->lay.bytes > limit) {
+            h->ref_in_smem = 0;
+            h->lay = make_layout(n, m, N, P, ncons, EX, 0, h->ITAB);
+        }
+        if ((size_t)h->lay.bytes > limit && EX > 0) {
+            CK(h, dalloc(&h->ex_glob, (size_t)B * EX));
+            h->lay = make_layout(n, m, N, P, ncons, 0, 0, h->ITAB);
+        }
     }
     size_t smem = (size_t)h->lay.bytes;
     if (smem > limit) {
@@ -348,7 +354,6 @@ int finalize(altro_handle_t h)
         return fail(h, ALTRO_ERR_UNSUPPORTED, buf);
     }
     h->smem = (int)smem;
-    h->kernel = find_kernel(n, m, T);
     if (!h->kernel) return fail(h, ALTRO_ERR_UNSUPPORTED, "no kernel for this configuration");
     CK(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa;

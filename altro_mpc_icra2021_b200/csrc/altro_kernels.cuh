@@ -50,6 +50,10 @@ struct Layout {
     int bytes;                       // total dynamic shared memory
 };
 
+#ifndef ALTRO_FIXED_ALL_SMEM
+#define ALTRO_FIXED_ALL_SMEM 1
+#endif
+
 // Arrays whose size depends only on (n, m) come first: in the kernels instantiated for a fixed <NX, NU> their
 // offsets are compile-time constants and every access folds into base + immediate.
 __host__ __device__ constexpr Layout fixed_layout(int n, int m)
@@ -118,6 +122,14 @@ struct Params {
 };
 
 #ifdef __CUDACC__
+
+// Constraint data and LTV dynamics always live in global memory: telling the compiler turns generic loads into LDG.
+template <class Tp>
+__device__ __forceinline__ const Tp *as_global(const Tp *p)
+{
+    __builtin_assume(__isGlobal(p));
+    return p;
+}
 
 template <int T>
 __device__ __forceinline__ void gsync()
@@ -232,6 +244,7 @@ __device__ __noinline__ bool ldl_solve_medium(double *L, double *linv, double *f
 // Per-instance context: shared-memory pointers and problem view.
 template <int NX, int NU, int T>
 struct Ctx {
+    static constexpr bool ALL_SMEM = NX > 0 && NU > 0 && ALTRO_FIXED_ALL_SMEM;
     const Params &P;
     int n, m, N, inst, tid, ncon;
     // shared memory
@@ -271,13 +284,19 @@ struct Ctx {
             linv = sm + l.linv; mu = sm + l.mu; bc = sm + l.bc; red = sm + l.red; X = sm + l.X;
         }
         U = sm + l.U; Xb = sm + l.Xb; Ub = sm + l.Ub;
-        if (P.ref_in_smem) { xr = sm + l.xr; ur = sm + l.ur; }
-        else {  // track windows / long horizons: read the reference through L1/L2 instead
-            xr = P.xref + (size_t)inst * N * n;
-            ur = P.uref + (size_t)inst * (N - 1) * m;
-        }
         K = sm + l.K; dv = sm + l.dv; lam = sm + l.lam;
-        ex = P.ex_glob ? P.ex_glob + (size_t)inst * P.EX : sm + l.ex;  // long horizons: expansion blocks in global memory
+        if constexpr (ALL_SMEM) {
+            // fixed-dimension kernels keep the reference window and the expansion blocks in shared memory, always
+            // (the host routes problems that do not fit to the run-time sized kernel): every access is an LDS/STS
+            xr = sm + l.xr; ur = sm + l.ur; ex = sm + l.ex;
+        } else {
+            if (P.ref_in_smem) { xr = sm + l.xr; ur = sm + l.ur; }
+            else {  // long horizons: read the reference through L1/L2 instead
+                xr = P.xref + (size_t)inst * N * n;
+                ur = P.uref + (size_t)inst * (N - 1) * m;
+            }
+            ex = P.ex_glob ? P.ex_glob + (size_t)inst * P.EX : sm + l.ex;  // longer still: expansion blocks in global memory
+        }
         ldiag = nullptr; itm = sm + l.itm;
         cd = reinterpret_cast<ConDesc *>(sm + l.cd);
         NT = n + n * n + m + m * m;
@@ -337,7 +356,7 @@ struct Ctx {
         const double *gU = P.U + (size_t)inst * (N - 1) * m;
         for (int i = tid; i < (N - 1) * m; i += T) U[i] = gU[i];
         const double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
-        if (P.ref_in_smem) {
+        if (ALL_SMEM || P.ref_in_smem) {
             for (int i = tid; i < N * n; i += T) xr[i] = gxr[i];
             for (int i = tid; i < (N - 1) * m; i += T) ur[i] = gur[i];
         }
@@ -375,7 +394,7 @@ struct Ctx {
     __device__ __forceinline__ double row_value(const ConDesc &c, const double *G, const double *h, const double *z,
                                                 int r) const
     {
-        if (c.rowsparse) return fma(c.rs_coef[r], z[c.inds[c.rs_col[r]]], h[r]);
+        if (c.rowsparse) return fma(as_global(c.rs_coef)[r], z[c.inds[as_global(c.rs_col)[r]]], h[r]);
         double acc = h[r];
         const double *g = G + r * c.w;
 #pragma unroll 1
@@ -389,7 +408,7 @@ struct Ctx {
         const ConDesc &c = cd[ci];
         if (k < c.k0 || k >= c.k1) return 0.0;
         const size_t di = con_idx(c, k);
-        const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
+        const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
         const double *z = c.side == ALTRO_STATE ? Xc + k * n : Uc + k * m;
         const double *l = lam + c.dual_off + (k - c.k0) * c.p;
         const double mu_c = mu[ci];
@@ -462,7 +481,7 @@ struct Ctx {
             const ConDesc &c = cd[ci];
             for (int k = c.k0 + tid; k < c.k1; k += T) {
                 const size_t di = con_idx(c, k);
-                const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
+                const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
                 if (c.sense == ALTRO_EQUALITY) {
                     for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
@@ -499,7 +518,7 @@ struct Ctx {
             const double mu_c = mu[ci];
             for (int k = c.k0 + tid; k < c.k1; k += T) {
                 const size_t di = con_idx(c, k);
-                const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
+                const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
                 double *l = lam + c.dual_off + (k - c.k0) * c.p;
                 if (c.sense == ALTRO_EQUALITY) {
@@ -541,7 +560,7 @@ struct Ctx {
             const int w = c.w, p = c.p;
             for (int k = c.k0 + tid; k < c.k1; k += T) {
                 const size_t di = con_idx(c, k);
-                const double *G = c.G + di * p * w, *h = c.h + di * p;
+                const double *G = as_global(c.G) + di * p * w, *h = as_global(c.h) + di * p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
                 const double *l = lam + c.dual_off + (k - c.k0) * p;
                 double *g = ex + c.ex_off + (k - c.k0) * c.ex_stride;
@@ -549,9 +568,9 @@ struct Ctx {
                 if (c.rowsparse) {
                     for (int j = 0; j < 2 * w; ++j) g[j] = 0.0;
                     for (int r = 0; r < p; ++r) {
-                        double v = row_value(c, G, h, z, r), cf = c.rs_coef[r];
+                        double v = row_value(c, G, h, z, r), cf = as_global(c.rs_coef)[r];
                         bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l[r] > 0.0);
-                        int col = c.rs_col[r];
+                        int col = as_global(c.rs_col)[r];
                         g[col] += cf * (l[r] + (act ? mu_c * v : 0.0));
                         H[col] += act ? cf * cf * mu_c : 0.0;
                     }
@@ -983,10 +1002,13 @@ struct Ctx {
     }
 
     // ---------------------------------------------------------------- rollouts (A.6, A.8)
-    __device__ void rollout_open_loop()
+    template <bool DS>
+    __device__ __forceinline__ void rollout_open_loop_impl()
     {
         for (int k = 0; k < N - 1; ++k) {
-            const double *A = Ak(k), *Bm = Bk(k), *d = dk(k);
+            const double *A = DS ? sA : as_global(P.A) + dyn_index(k) * n * n;
+            const double *Bm = DS ? sB : as_global(P.Bm) + dyn_index(k) * n * m;
+            const double *d = DS ? sd : as_global(P.d) + dyn_index(k) * n;
             for (int i = tid; i < n; i += T) {
                 double acc = d[i];
                 for (int j = 0; j < n; ++j) acc = fma(A[i * n + j], X[k * n + j], acc);
@@ -996,15 +1018,23 @@ struct Ctx {
             gsync<T>();
         }
     }
+    __device__ void rollout_open_loop()
+    {
+        if (P.dyn_in_smem) rollout_open_loop_impl<true>();
+        else rollout_open_loop_impl<false>();
+    }
 
     // Closed-loop rollout with step alpha into Xb, Ub. Returns false if a state leaves the box.
-    __device__ bool rollout_alpha(double alpha)
+    template <bool DS>
+    __device__ __forceinline__ bool rollout_alpha_impl(double alpha)
     {
         for (int i = tid; i < n; i += T) Xb[i] = X[i];
         gsync<T>();
         double bad = 0.0;
         for (int k = 0; k < N - 1; ++k) {
-            const double *A = Ak(k), *Bm = Bk(k), *d = dk(k);
+            const double *A = DS ? sA : as_global(P.A) + dyn_index(k) * n * n;
+            const double *Bm = DS ? sB : as_global(P.Bm) + dyn_index(k) * n * m;
+            const double *d = DS ? sd : as_global(P.d) + dyn_index(k) * n;
             const double *Kk = K + k * m * n;
             for (int i = tid; i < m; i += T) {
                 double acc = fma(alpha, dv[k * m + i], U[k * m + i]);
@@ -1022,6 +1052,10 @@ struct Ctx {
             gsync<T>();
         }
         return gmax<T>(bad, red) == 0.0;
+    }
+    __device__ bool rollout_alpha(double alpha)
+    {
+        return P.dyn_in_smem ? rollout_alpha_impl<true>(alpha) : rollout_alpha_impl<false>(alpha);
     }
 
     __device__ void copy_traj(double *Xd, double *Ud, const double *Xs, const double *Us)
@@ -1102,10 +1136,11 @@ struct Ctx {
         }
         if (P.trackX) {
             const int k0 = P.kidx[inst] + st + 1;
-            if (P.ref_in_smem) {
-                for (int i = tid; i < N * n; i += T) xr[i] = P.trackX[(size_t)min(k0 + i / n, P.Nt - 1) * n + i % n];
-                for (int i = tid; i < (N - 1) * m; i += T) ur[i] = P.trackU[(size_t)min(k0 + i / m, P.Nt - 2) * m + i % m];
-            } else {  // the device track is padded with N copies of its last knot: the window is one contiguous slice
+            if (ALL_SMEM || P.ref_in_smem) {  // the device track is padded with N copies of its last knot: one contiguous slice
+                const double *wx = P.trackX + (size_t)min(k0, P.Nt) * n, *wu = P.trackU + (size_t)min(k0, P.Nt - 1) * m;
+                for (int i = tid; i < N * n; i += T) xr[i] = wx[i];
+                for (int i = tid; i < (N - 1) * m; i += T) ur[i] = wu[i];
+            } else {
                 xr = const_cast<double *>(P.trackX) + (size_t)min(k0, P.Nt) * n;
                 ur = const_cast<double *>(P.trackU) + (size_t)min(k0, P.Nt - 1) * m;
             }
