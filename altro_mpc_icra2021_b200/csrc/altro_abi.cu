@@ -78,6 +78,7 @@ struct altro_handle_s {
     int threads_req = 0, threads = 0, smem = 0, regs = 0, ctas_per_sm = 0, num_sms = 0, dyn_in_smem = 0, ref_in_smem = 1;
     const void *kernel = nullptr;
     Layout lay;
+    int spec = 0, spec_req = -1;  // speculative line search: in use / requested (-1 = automatic)
 };
 
 namespace {
@@ -320,9 +321,10 @@ int finalize(altro_handle_t h)
     const int maxdim = std::max(n, m);
     int T = h->threads_req;
     if (const char *e = getenv("ALTRO_B200_THREADS")) T = atoi(e);
-    if (T == 0)  // measured on B200 (scripts/dev_perf.py sweeps): one warp for tiny blocks, 2 warps for 12-dimensional
-                 // problems, 4 when the horizon is long (flexible satellite), more for the big run-time sized ones
-        T = maxdim <= 8 ? 32 : maxdim <= 16 ? (N >= 60 ? 128 : 64) : maxdim <= 32 ? 128 : 256;
+    if (T == 0)  // measured on B200 (scripts/dev_perf.py sweeps): 2 warps up to 16 dimensions (the second warp takes every
+                 // other tensor tile and line-search trial), 4 when the horizon is long (flexible satellite), more for
+                 // the big run-time sized ones
+        T = maxdim <= 16 ? (N >= 60 ? 128 : 64) : maxdim <= 32 ? 128 : 256;
     if (T != 32 && T != 64 && T != 128 && T != 256) return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 32, 64, 128 or 256");
     h->threads = T;
     h->dyn_in_smem = (!h->dyn_per_knot && !h->dyn_per_instance) ? 1 : 0;
@@ -334,9 +336,26 @@ int finalize(altro_handle_t h)
     // expansion blocks too.
     h->kernel = find_kernel(n, m, T);
     h->ref_in_smem = 1;
+    // Speculative line search (one trial per warp, see forward_pass_spec) needs one more candidate set per extra warp:
+    // on unless that costs resident CTAs (measured: random_linear loses more from 6 -> 5 CTAs/SM than it gains).
     h->lay = make_layout(n, m, N, P, ncons, EX, 1, h->ITAB);
+    h->spec = 0;
+    if (T > 32) {
+        const Layout ls = make_layout(n, m, N, P, ncons, EX, 1, h->ITAB, T / 32 - 1);
+        int want = h->spec_req;
+        if (const char *e = getenv("ALTRO_B200_SPEC")) want = atoi(e) ? 1 : 0;
+        if (want < 0 && (size_t)ls.bytes <= limit) {
+            int nb0 = 0, nb1 = 0;
+            CK(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ls.bytes));
+            CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, h->kernel, T, (size_t)h->lay.bytes));
+            CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, h->kernel, T, (size_t)ls.bytes));
+            want = nb1 >= nb0 ? 1 : 0;
+        }
+        if (want > 0 && (size_t)ls.bytes <= limit) { h->spec = 1; h->lay = ls; }
+    }
     if ((size_t)h->lay.bytes > limit || !ALTRO_FIXED_ALL_SMEM) {
         if ((size_t)h->lay.bytes > limit) h->kernel = kernel_0_0(T);
+        h->spec = 0;
         if (h->trackX || (size_t)h->lay.bytes > limit) {
             h->ref_in_smem = 0;
             h->lay = make_layout(n, m, N, P, ncons, EX, 0, h->ITAB);
@@ -807,6 +826,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     P.con = h->con_dev;
     P.itab = h->itab_dev;
     P.lay = h->lay;
+    P.spec = h->spec;
     P.o = h->opts;
     P.dyn_slots = h->dyn_slots; P.sched_len = h->sched_len; P.step0 = h->step_abs; P.dyn_sched = h->sched;
     P.steps = steps; P.shift = shift; P.noise_mode = h->noise_mode; P.Nt = h->Nt;
@@ -1098,6 +1118,23 @@ int altro_set_launch_config(altro_handle_t h, int threads)
     if (threads != 0 && threads != 32 && threads != 64 && threads != 128 && threads != 256)
         return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 0 (auto), 32, 64, 128 or 256");
     h->threads_req = threads;
+    return ALTRO_OK;
+}
+
+int altro_set_line_search_mode(altro_handle_t h, int speculative)
+{
+    REQ(h);
+    if (h->finalized) return fail(h, ALTRO_ERR_STATE, "launch configuration is fixed after the first solve");
+    h->spec_req = speculative < 0 ? -1 : (speculative ? 1 : 0);
+    return ALTRO_OK;
+}
+
+int altro_get_line_search_mode(altro_handle_t h, int *speculative)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (speculative) *speculative = h->spec;
     return ALTRO_OK;
 }
 

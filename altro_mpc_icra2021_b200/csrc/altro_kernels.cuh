@@ -46,7 +46,7 @@ struct ConDesc {
 // operand instead of re-deriving a chain of run-time products (11 % of all executed instructions before).
 struct Layout {
     int Qd, Qfd, Rd, sA, sB, sd, X, U, Xb, Ub, xr, ur, K, dv, lam, mu, ex, S, SA, Qxx, SB, Qux, T1, Quu, L, s, Qx, Qu,
-        t1, linv, red, bc, itm, cd;  // cd: offset (in doubles) of the ConDesc array, followed by the gather tables
+        t1, linv, red, bc, itm, cand, cd;  // cd: offset (in doubles) of the ConDesc array, followed by the gather tables
     int bytes;                       // total dynamic shared memory
 };
 
@@ -65,12 +65,13 @@ __host__ __device__ constexpr Layout fixed_layout(int n, int m)
     l.S = q; q += n * n; l.SA = q; q += n * n; l.Qxx = q; q += n * n; l.SB = q; q += n * m; l.Qux = q; q += m * n;
     l.T1 = q; q += m * n; l.Quu = q; q += m * m; l.L = q; q += m * m;
     l.s = q; q += n; l.Qx = q; q += n; l.Qu = q; q += m; l.t1 = q; q += m; l.linv = q; q += m;
-    l.mu = q; q += MAX_CON; l.bc = q; q += 8; l.red = q; q += 9;  // up to 8 warps + 1
+    l.mu = q; q += MAX_CON; l.bc = q; q += 24; l.red = q; q += 9;  // 8 broadcast slots + 16 speculative line-search results; 8 warps + 1
     l.X = q;
     return l;
 }
 
-__host__ __device__ inline Layout make_layout(int n, int m, int N, int P, int ncon, int EX, int ref_in_smem, int ITAB)
+__host__ __device__ inline Layout make_layout(int n, int m, int N, int P, int ncon, int EX, int ref_in_smem, int ITAB,
+                                              int spec_sets = 0)
 {
     Layout l = fixed_layout(n, m);
     int q = l.X;
@@ -82,6 +83,8 @@ __host__ __device__ inline Layout make_layout(int n, int m, int N, int P, int nc
     l.lam = take(P);
     l.ex = take(EX);  // EX = 0 when the expansion blocks live in global memory
     l.itm = take(N * (1 + ncon));
+    // speculative line search: one extra (Xb, Ub, itm) set per additional warp
+    l.cand = take(spec_sets * (N * n + (N - 1) * m + N * (1 + ncon)));
     l.cd = q;
     size_t b = (size_t)q * sizeof(double) + (size_t)(ncon > 0 ? ncon : 1) * sizeof(ConDesc) + (size_t)ITAB * sizeof(int);
     l.bytes = (int)((b + 15) & ~(size_t)15);
@@ -118,6 +121,7 @@ struct Params {
     const ConDesc *con;
     const int *itab;  // gather lists built by the host: gptr[NT+1] then gsrc[]
     Layout lay;
+    int spec;  // line-search trials evaluated concurrently, one per warp (0 = sequential)
     altro_opts_t o;
 };
 
@@ -142,16 +146,16 @@ __device__ __forceinline__ void gsync()
 // xor-butterfly over the 32 partials.  The summation order does not depend on T, so the CPU oracle
 // can reproduce every cost / gradient value bit for bit.  arr must be visible to warp 0 on entry.
 template <int T>
-__device__ __forceinline__ double csum(const double *arr, int count, double *bc)
+__device__ __forceinline__ double csum(const double *arr, int count, double *bc, int tid)
 {
     double v = 0.0;
-    if (T == 32 || threadIdx.x < 32) {
-        for (int i = threadIdx.x; i < count; i += 32) v += arr[i];
+    if (T == 32 || tid < 32) {
+        for (int i = tid; i < count; i += 32) v += arr[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     }
     if (T == 32) return v;
-    if (threadIdx.x == 0) bc[2] = v;
+    if (tid == 0) bc[2] = v;
     __syncthreads();
     v = bc[2];
     __syncthreads();
@@ -246,6 +250,8 @@ template <int NX, int NU, int T>
 struct Ctx {
     static constexpr bool ALL_SMEM = NX > 0 && NU > 0 && ALTRO_FIXED_ALL_SMEM;
     const Params &P;
+    unsigned char *smem_base;
+    double *specr;  // [2 W] (ok, J) of the speculative line-search trials
     int n, m, N, inst, tid, ncon;
     // shared memory
     double *Qd, *Qfd, *Rd, *sA, *sB, *sd;
@@ -261,7 +267,7 @@ struct Ctx {
     const int *sched;  // this instance's dynamics schedule at the current MPC step, or nullptr
     int kcur;          // this instance's position on the shared timelines (reference track, track constraints)
 
-    __device__ Ctx(const Params &P_, unsigned char *raw) : P(P_)
+    __device__ Ctx(const Params &P_, unsigned char *raw) : P(P_), smem_base(raw)
     {
         n = NX ? NX : P.n;
         m = NU ? NU : P.m;
@@ -297,7 +303,7 @@ struct Ctx {
             }
             ex = P.ex_glob ? P.ex_glob + (size_t)inst * P.EX : sm + l.ex;  // longer still: expansion blocks in global memory
         }
-        ldiag = nullptr; itm = sm + l.itm;
+        ldiag = nullptr; itm = sm + l.itm; specr = bc + 8;
         cd = reinterpret_cast<ConDesc *>(sm + l.cd);
         NT = n + n * n + m + m * m;
         gptr = reinterpret_cast<int *>(cd + (ncon > 0 ? ncon : 1));
@@ -463,14 +469,14 @@ struct Ctx {
         for (int j = 0; j < ncon; ++j)
             for (int k = tid; k < N; k += T) itm[(j + 1) * N + k] = con_cost(j, k, Xc, Uc);
         gsync<T>();
-        return csum<T>(itm, items, bc);
+        return csum<T>(itm, items, bc, tid);
     }
 
     __device__ double objective_cost() const
     {
         for (int k = tid; k < N; k += T) itm[k] = stage_cost(k, X, U);
         gsync<T>();
-        return csum<T>(itm, N, bc);
+        return csum<T>(itm, N, bc, tid);
     }
 
     // max_violation
@@ -1067,6 +1073,9 @@ struct Ctx {
 
     __device__ double forward_pass(double dV1, double dV2, double J_prev, double &rho, double &drho, int &trials)
     {
+        if constexpr (T > 32) {
+            if (P.spec) return forward_pass_spec(dV1, dV2, J_prev, rho, drho, trials);
+        }
         double J = INFINITY, alpha = 1.0, z = -1.0;
         int iter = 0;
         while ((z <= P.o.line_search_lower_bound || z > P.o.line_search_upper_bound) && J >= J_prev) {
@@ -1093,6 +1102,72 @@ struct Ctx {
         return J;
     }
 
+    // Speculative line search: warp w rolls out and costs the step alpha 2^-w into its own candidate buffers while
+    // the other warps do theirs, then every thread replays the sequential acceptance test over the results in order.
+    // Same accepted step, same trajectory, same trial count as forward_pass (a trial's value does not depend on
+    // the number of threads that compute it); the trials past the accepted one are wasted work traded for latency.
+    __device__ double forward_pass_spec(double dV1, double dV2, double J_prev, double &rho, double &drho, int &trials)
+    {
+        constexpr int W = T / 32;
+        const int warp = tid >> 5, lane = tid & 31;
+        const int set = N * n + (N - 1) * m + N * (1 + ncon);
+        double *Xb0 = reinterpret_cast<double *>(smem_base) + P.lay.Xb, *Ub0 = reinterpret_cast<double *>(smem_base) + P.lay.Ub;
+        double *itm0 = itm;
+        double *cs = reinterpret_cast<double *>(smem_base) + P.lay.cand + (warp > 0 ? (warp - 1) * set : 0);
+        Ctx<NX, NU, 32> v(P, smem_base);
+        v.tid = lane;
+        v.kcur = kcur;
+        v.sched = sched;
+        if (warp > 0) { v.Xb = cs; v.Ub = cs + N * n; v.itm = cs + N * n + (N - 1) * m; }
+        else { v.Xb = Xb0; v.Ub = Ub0; v.itm = itm0; }
+        double J = INFINITY, alpha = 1.0, z = -1.0;
+        int iter = 0, chosen = -1;
+        const double lo = P.o.line_search_lower_bound, hi = P.o.line_search_upper_bound;
+        while ((z <= lo || z > hi) && J >= J_prev) {
+            if (iter > P.o.iterations_linesearch) {
+                Xb = Xb0; Ub = Ub0;
+                copy_traj(Xb, Ub, X, U);
+                J = al_cost(Xb, Ub);
+                reg_increase(rho, drho);
+                rho += P.o.bp_reg_fp;
+                return J;
+            }
+            const long long cr = clock64();
+            {
+                double aw = alpha;
+                for (int q = 0; q < warp; ++q) aw *= 0.5;
+                double ok = 0.0, Jw = 0.0;
+                if (iter + warp <= P.o.iterations_linesearch) {
+                    ok = v.rollout_alpha(aw) ? 1.0 : 0.0;
+                    if (ok != 0.0) Jw = v.al_cost(v.Xb, v.Ub);
+                }
+                if (lane == 0) { specr[2 * warp] = ok; specr[2 * warp + 1] = Jw; }
+            }
+            __syncthreads();
+            ph_roll += clock64() - cr;
+            for (int w = 0; w < W; ++w) {
+                if (!((z <= lo || z > hi) && J >= J_prev)) break;
+                if (iter > P.o.iterations_linesearch) break;
+                ++trials;
+                if (specr[2 * w] != 0.0) {
+                    J = specr[2 * w + 1];
+                    const double expected = -alpha * (dV1 + alpha * dV2);
+                    z = expected > 0.0 ? (J_prev - J) / expected : -1.0;
+                    chosen = w;
+                }
+                ++iter;
+                alpha *= 0.5;
+            }
+            __syncthreads();
+        }
+        // the accepted candidate becomes (Xb, Ub); the caller copies it into (X, U)
+        if (chosen > 0) {
+            double *cc = reinterpret_cast<double *>(smem_base) + P.lay.cand + (chosen - 1) * set;
+            Xb = cc; Ub = cc + N * n;
+        } else { Xb = Xb0; Ub = Ub0; }
+        return J;
+    }
+
     __device__ double gradient_todorov() const
     {
         for (int k = tid; k < N - 1; k += T) {
@@ -1101,7 +1176,7 @@ struct Ctx {
             itm[k] = mx;
         }
         gsync<T>();
-        return csum<T>(itm, N - 1, bc) / (double)(N - 1);
+        return csum<T>(itm, N - 1, bc, tid) / (double)(N - 1);
     }
 
     // ---------------------------------------------------------------- solve! (A.4 - A.6)

@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "altro_get_timing", "altro_get_phase_cycles", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0", "altro_mpc_run",
     "altro_get_run_results",
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
+    "altro_set_line_search_mode", "altro_get_line_search_mode",
     "altro_measure_peaks",
 ]
 
@@ -107,7 +108,8 @@ class SolverStats:
 
 class ALTROSolver:
     def __init__(self, prob: Problem, opts: Optional[SolverOptions] = None, device: int = 0,
-                 threads_per_instance: int = 0, stream: Optional[int] = None, pin: bool = False, **kwargs):
+                 threads_per_instance: int = 0, stream: Optional[int] = None, pin: bool = False,
+                 speculative_line_search: Optional[bool] = None, **kwargs):
         self.lib = load_library()
         self.prob = prob
         self.opts = (opts or SolverOptions()).copy()
@@ -122,6 +124,8 @@ class ALTROSolver:
             self._ck(self.lib.altro_set_stream(self.h, C.c_void_p(stream)))
         if threads_per_instance:
             self._ck(self.lib.altro_set_launch_config(self.h, threads_per_instance))
+        if speculative_line_search is not None:
+            self._ck(self.lib.altro_set_line_search_mode(self.h, int(bool(speculative_line_search))))
         self._ck(self.lib.altro_set_cost_diag(self.h, _p(prob.obj.Q), _p(prob.obj.R), _p(prob.obj.Qf)))
         for c in prob.constraints.flat:
             cid = C.c_int()
@@ -380,7 +384,11 @@ class ALTROSolver:
         v = [C.c_int() for _ in range(5)]
         self._ck(self.lib.altro_get_launch_info(self.h, *[C.byref(x) for x in v]))
         keys = ("threads_per_instance", "smem_bytes", "regs_per_thread", "ctas_per_sm", "num_sms")
-        return {k: x.value for k, x in zip(keys, v)}
+        info = {k: x.value for k, x in zip(keys, v)}
+        spec = C.c_int()
+        self._ck(self.lib.altro_get_line_search_mode(self.h, C.byref(spec)))
+        info["speculative_line_search"] = bool(spec.value)
+        return info
 
     def all_succeeded(self) -> bool:
         return bool(np.all(self.stats.status == SOLVE_SUCCEEDED))

@@ -196,6 +196,15 @@ int altro_set_launch_config(altro_handle_t h, int threads_per_instance);
 int altro_get_launch_info(altro_handle_t h, int *threads_per_instance, int *smem_bytes, int *regs_per_thread,
                           int *ctas_per_sm, int *num_sms);
 
+/* Line search of the forward pass (Altro ilqr/forwardpass.jl, SURVEY.md A.8: alpha = 1, 1/2, 1/4, ... until the
+ * first step passes the expected-decrease test). speculative = 1: each warp of the instance rolls out and costs
+ * one of the next threads/32 trial steps at the same time and the acceptance test is replayed over them in
+ * order -- same accepted step, trajectory and trial count, lower latency; 0: one trial after the other;
+ * -1 (default): speculative when the extra candidate buffers do not cost resident CTAs. Set before the first
+ * solve. The getter reports what the finalized handle uses. */
+int altro_set_line_search_mode(altro_handle_t h, int speculative);
+int altro_get_line_search_mode(altro_handle_t h, int *speculative);
+
 /* FP64 roofline denominators measured on `device`: dependent-free DFMA stream and
  * mma.sync m8n8k4 f64 stream (TFLOP/s), and a device copy (GB/s). Any may be NULL. */
 int altro_measure_peaks(int device, double *dfma_tflops, double *dmma_tflops, double *copy_gbs);

@@ -95,6 +95,24 @@ def test_threads_per_instance_do_not_change_bits(threads):
     solve_both(prob, opts, threads_per_instance=threads)
 
 
+@pytest.mark.parametrize("threads", [64, 128, 256])
+@pytest.mark.parametrize("spec", [False, True])
+@pytest.mark.parametrize("family", ["rocket", "quadruped_soc", "random_linear"])
+def test_speculative_line_search_does_not_change_bits(family, spec, threads):
+    """One line-search trial per warp (forward_pass_spec) vs one after the other: same accepted step, same
+    trajectories, same trial counts -- against the oracle, which only knows the sequential search."""
+    if family == "rocket":
+        cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+        prob, opts, _, _ = cases.case_rocket_mpc(cold["X"], cold["U"], batch=32)
+    elif family == "random_linear":
+        prob, opts, _, _ = cases.case_random_linear(batch=32)
+    else:
+        prob, opts, _, _ = cases.case_quadruped(False, batch=32)
+    _, g, o = solve_both(prob, opts, threads_per_instance=threads, speculative_line_search=spec)
+    assert g.launch_info()["speculative_line_search"] == spec
+    assert np.array_equal(g.stats.ls_trials, o.stats.ls_trials)
+
+
 def test_runtime_dimension_kernel_matches_compiled_dimensions(monkeypatch):
     prob, opts, _, _ = cases.case_random_linear(batch=8)
     ref = copy.deepcopy(prob)
