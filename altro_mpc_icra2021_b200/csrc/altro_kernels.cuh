@@ -150,6 +150,7 @@ __device__ __forceinline__ double csum(const double *arr, int count, double *bc,
 {
     double v = 0.0;
     if (T == 32 || tid < 32) {
+#pragma unroll 1
         for (int i = tid; i < count; i += 32) v += arr[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -345,35 +346,49 @@ struct Ctx {
     // ---------------------------------------------------------------- load / store
     __device__ void load()
     {
+#pragma unroll 1
         for (int i = tid; i < n; i += T) { Qd[i] = P.Q[i]; Qfd[i] = P.Qf[i]; }
+#pragma unroll 1
         for (int i = tid; i < m; i += T) Rd[i] = P.R[i];
         if (P.dyn_in_smem) {  // shared LTI model
+#pragma unroll 1
             for (int i = tid; i < n * n; i += T) sA[i] = P.A[i];
+#pragma unroll 1
             for (int i = tid; i < n * m; i += T) sB[i] = P.Bm[i];
+#pragma unroll 1
             for (int i = tid; i < n; i += T) sd[i] = P.d[i];
         }
         if (P.steps > 0) {  // closed-loop run: start from the previous solution (its x_1 is the next x_0)
             const double *gX = P.X + (size_t)inst * N * n;
+#pragma unroll 1
             for (int i = tid; i < N * n; i += T) X[i] = gX[i];
         } else {
             const double *gx0 = P.x0 + (size_t)inst * n;
+#pragma unroll 1
             for (int i = tid; i < n; i += T) X[i] = gx0[i];
         }
         const double *gU = P.U + (size_t)inst * (N - 1) * m;
+#pragma unroll 1
         for (int i = tid; i < (N - 1) * m; i += T) U[i] = gU[i];
         const double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
         if (ALL_SMEM || P.ref_in_smem) {
+#pragma unroll 1
             for (int i = tid; i < N * n; i += T) xr[i] = gxr[i];
+#pragma unroll 1
             for (int i = tid; i < (N - 1) * m; i += T) ur[i] = gur[i];
         }
         const double *gl = P.lam + (size_t)inst * P.P;
         const bool rd = P.o.reset_duals != 0;
+#pragma unroll 1
         for (int i = tid; i < P.P; i += T) lam[i] = rd ? 0.0 : gl[i];
+#pragma unroll 1
         for (int i = tid; i < MAX_CON; i += T) mu[i] = P.o.penalty_initial;
         const int words = ncon * (int)(sizeof(ConDesc) / sizeof(int));
         const int *src = reinterpret_cast<const int *>(P.con);
         int *dst = reinterpret_cast<int *>(cd);
+#pragma unroll 1
         for (int i = tid; i < words; i += T) dst[i] = src[i];
+#pragma unroll 1
         for (int i = tid; i < P.ITAB; i += T) gptr[i] = P.itab[i];
         gsync<T>();
     }
@@ -381,15 +396,21 @@ struct Ctx {
     __device__ void store()
     {
         double *gX = P.X + (size_t)inst * N * n, *gU = P.U + (size_t)inst * (N - 1) * m;
+#pragma unroll 1
         for (int i = tid; i < N * n; i += T) gX[i] = X[i];
+#pragma unroll 1
         for (int i = tid; i < (N - 1) * m; i += T) gU[i] = U[i];
         double *gl = P.lam + (size_t)inst * P.P;
+#pragma unroll 1
         for (int i = tid; i < P.P; i += T) gl[i] = lam[i];
         if (P.steps > 0) {  // closed-loop run: the handle's x0 and reference window follow the plant
+#pragma unroll 1
             for (int i = tid; i < n; i += T) P.x0[(size_t)inst * n + i] = X[i];
             if (P.trackX) {
                 double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
+#pragma unroll 1
                 for (int i = tid; i < N * n; i += T) gxr[i] = xr[i];
+#pragma unroll 1
                 for (int i = tid; i < (N - 1) * m; i += T) gur[i] = ur[i];
             }
         }
@@ -420,11 +441,13 @@ struct Ctx {
         const double mu_c = mu[ci];
         double J = 0.0;
         if (c.sense == ALTRO_EQUALITY) {
+#pragma unroll 1
             for (int r = 0; r < c.p; ++r) {
                 double v = row_value(c, G, h, z, r);
                 J += l[r] * v + 0.5 * mu_c * v * v;
             }
         } else if (c.sense == ALTRO_INEQUALITY) {
+#pragma unroll 1
             for (int r = 0; r < c.p; ++r) {
                 double v = row_value(c, G, h, z, r);
                 bool act = (v >= 0.0) || (l[r] > 0.0);
@@ -432,6 +455,7 @@ struct Ctx {
             }
         } else {
             double a2 = 0.0, t = 0.0, nl = 0.0;
+#pragma unroll 1
             for (int r = 0; r < c.p; ++r) {
                 double lb = l[r] - mu_c * row_value(c, G, h, z, r);
                 nl += l[r] * l[r];
@@ -465,8 +489,11 @@ struct Ctx {
     __device__ double al_cost(const double *Xc, const double *Uc) const
     {
         const int items = N * (1 + ncon);
+#pragma unroll 1
         for (int k = tid; k < N; k += T) itm[k] = stage_cost(k, Xc, Uc);
+#pragma unroll 1
         for (int j = 0; j < ncon; ++j)
+#pragma unroll 1
             for (int k = tid; k < N; k += T) itm[(j + 1) * N + k] = con_cost(j, k, Xc, Uc);
         gsync<T>();
         return csum<T>(itm, items, bc, tid);
@@ -474,6 +501,7 @@ struct Ctx {
 
     __device__ double objective_cost() const
     {
+#pragma unroll 1
         for (int k = tid; k < N; k += T) itm[k] = stage_cost(k, X, U);
         gsync<T>();
         return csum<T>(itm, N, bc, tid);
@@ -483,18 +511,23 @@ struct Ctx {
     __device__ double max_violation() const
     {
         double v = 0.0;
+#pragma unroll 1
         for (int ci = 0; ci < ncon; ++ci) {
             const ConDesc &c = cd[ci];
+#pragma unroll 1
             for (int k = c.k0 + tid; k < c.k1; k += T) {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
                 if (c.sense == ALTRO_EQUALITY) {
+#pragma unroll 1
                     for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
                 } else if (c.sense == ALTRO_INEQUALITY) {
+#pragma unroll 1
                     for (int r = 0; r < c.p; ++r) v = fmax(v, row_value(c, G, h, z, r));
                 } else {
                     double a2 = 0.0, t = 0.0;
+#pragma unroll 1
                     for (int r = 0; r < c.p; ++r) {
                         double cv = row_value(c, G, h, z, r);
                         if (r < c.p - 1) a2 += cv * cv;
@@ -504,9 +537,11 @@ struct Ctx {
                     if (!P.o.soc_viol_proj) {
                         v = fmax(v, a - t);
                     } else if (a <= -t) {  // projection is 0: distance = |c|_inf
+#pragma unroll 1
                         for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
                     } else if (a > t) {  // c - Pi(c) = ((1-cf) v, t - cf a)
                         double cf = 0.5 * (1.0 + t / a);
+#pragma unroll 1
                         for (int r = 0; r < c.p - 1; ++r) v = fmax(v, fabs((1.0 - cf) * row_value(c, G, h, z, r)));
                         v = fmax(v, fabs(t - cf * a));
                     }
@@ -519,22 +554,27 @@ struct Ctx {
     // dual_update!: one (block, knot) per thread.
     __device__ void dual_update()
     {
+#pragma unroll 1
         for (int ci = 0; ci < ncon; ++ci) {
             const ConDesc &c = cd[ci];
             const double mu_c = mu[ci];
+#pragma unroll 1
             for (int k = c.k0 + tid; k < c.k1; k += T) {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
                 double *l = lam + c.dual_off + (k - c.k0) * c.p;
                 if (c.sense == ALTRO_EQUALITY) {
+#pragma unroll 1
                     for (int r = 0; r < c.p; ++r)
                         l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, r), -P.o.dual_max), P.o.dual_max);
                 } else if (c.sense == ALTRO_INEQUALITY) {
+#pragma unroll 1
                     for (int r = 0; r < c.p; ++r)
                         l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, r), 0.0), P.o.dual_max);
                 } else {
                     double a2 = 0.0, t = 0.0;
+#pragma unroll 1
                     for (int r = 0; r < c.p; ++r) {
                         double lb = l[r] - mu_c * row_value(c, G, h, z, r);
                         l[r] = lb;
@@ -543,9 +583,11 @@ struct Ctx {
                     }
                     double a = sqrt(a2);
                     if (a <= -t) {
+#pragma unroll 1
                         for (int r = 0; r < c.p; ++r) l[r] = 0.0;
                     } else if (a > t) {
                         double cf = 0.5 * (1.0 + t / a);
+#pragma unroll 1
                         for (int r = 0; r < c.p - 1; ++r) l[r] *= cf;
                         l[c.p - 1] = cf * a;
                     }
@@ -560,10 +602,12 @@ struct Ctx {
     // every (block, knot) into the expansion scratch; one work item per thread.
     __device__ void expand_constraints()
     {
+#pragma unroll 1
         for (int ci = 0; ci < ncon; ++ci) {
             const ConDesc &c = cd[ci];
             const double mu_c = mu[ci];
             const int w = c.w, p = c.p;
+#pragma unroll 1
             for (int k = c.k0 + tid; k < c.k1; k += T) {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * p * w, *h = as_global(c.h) + di * p;
@@ -572,7 +616,9 @@ struct Ctx {
                 double *g = ex + c.ex_off + (k - c.k0) * c.ex_stride;
                 double *H = g + w;
                 if (c.rowsparse) {
+#pragma unroll 1
                     for (int j = 0; j < 2 * w; ++j) g[j] = 0.0;
+#pragma unroll 1
                     for (int r = 0; r < p; ++r) {
                         double v = row_value(c, G, h, z, r), cf = as_global(c.rs_coef)[r];
                         bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l[r] > 0.0);
@@ -582,20 +628,26 @@ struct Ctx {
                     }
                 } else if (c.sense != ALTRO_SECOND_ORDER_CONE) {
                     double y[PMAX], D[PMAX];
+#pragma unroll 1
                     for (int r = 0; r < p; ++r) {
                         double v = row_value(c, G, h, z, r);
                         bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l[r] > 0.0);
                         y[r] = l[r] + (act ? mu_c * v : 0.0);
                         D[r] = act ? mu_c : 0.0;
                     }
+#pragma unroll 1
                     for (int j = 0; j < w; ++j) {
                         double acc = 0.0;
+#pragma unroll 1
                         for (int r = 0; r < p; ++r) acc = fma(G[r * w + j], y[r], acc);
                         g[j] = acc;
                     }
+#pragma unroll 1
                     for (int i = 0, at = 0; i < w; ++i)
+#pragma unroll 1
                         for (int j = i; j < w; ++j, ++at) {
                             double acc = 0.0;
+#pragma unroll 1
                             for (int r = 0; r < p; ++r) acc = fma(G[r * w + i] * D[r], G[r * w + j], acc);
                             H[at] = acc;
                         }
@@ -603,6 +655,7 @@ struct Ctx {
                     // lb = lam - mu c ; Pi(lb) ; g = -G' Pi(lb) ; H = mu G' dPi(lb) G  (structured)
                     double lb[PMAX], q[DENSE_W];
                     double a2 = 0.0;
+#pragma unroll 1
                     for (int r = 0; r < p; ++r) {
                         lb[r] = l[r] - mu_c * row_value(c, G, h, z, r);
                         if (r < p - 1) a2 += lb[r] * lb[r];
@@ -610,16 +663,22 @@ struct Ctx {
                     const double t = lb[p - 1], a = sqrt(a2);
                     const double *gt = G + (p - 1) * w;
                     if (a <= -t) {
+#pragma unroll 1
                         for (int j = 0; j < c.ex_stride; ++j) g[j] = 0.0;
                     } else if (a <= t) {
+#pragma unroll 1
                         for (int j = 0; j < w; ++j) {
                             double acc = 0.0;
+#pragma unroll 1
                             for (int r = 0; r < p; ++r) acc = fma(G[r * w + j], lb[r], acc);
                             g[j] = -acc;
                         }
+#pragma unroll 1
                         for (int i = 0, at = 0; i < w; ++i)
+#pragma unroll 1
                             for (int j = i; j < w; ++j, ++at) {
                                 double acc = 0.0;
+#pragma unroll 1
                                 for (int r = 0; r < p; ++r) acc = fma(G[r * w + i], G[r * w + j], acc);
                                 H[at] = mu_c * acc;
                             }
@@ -627,18 +686,24 @@ struct Ctx {
                         const double ia = 1.0 / a, cf = 0.5 * (1.0 + t * ia);
                         const double cx = P.o.soc_hess_exact ? cf : cf * cf;
                         // q = G' [xhat; 1],  xhat = v / a
+#pragma unroll 1
                         for (int j = 0; j < w; ++j) {
                             double acc = 0.0;
+#pragma unroll 1
                             for (int r = 0; r < p - 1; ++r) acc = fma(G[r * w + j], lb[r], acc);
                             q[j] = acc * ia;  // omega_hat
                         }
+#pragma unroll 1
                         for (int i = 0, at = 0; i < w; ++i)
+#pragma unroll 1
                             for (int j = i; j < w; ++j, ++at) {
                                 double gg = 0.0;
+#pragma unroll 1
                                 for (int r = 0; r < p - 1; ++r) gg = fma(G[r * w + i], G[r * w + j], gg);
                                 double qi = q[i] + gt[i], qj = q[j] + gt[j];
                                 H[at] = mu_c * (cx * (gg - q[i] * q[j]) + 0.5 * qi * qj);
                             }
+#pragma unroll 1
                         for (int j = 0; j < w; ++j) g[j] = -cf * a * (q[j] + gt[j]);
                     }
                 }
@@ -651,6 +716,7 @@ struct Ctx {
     // in ascending block order (the order the oracle's scatter uses).
     __device__ __forceinline__ double gather(int t, int k, double base) const
     {
+#pragma unroll 1
         for (int q = gptr[t]; q < gptr[t + 1]; ++q) {
             const int src = gsrc[q];
             const ConDesc &c = cd[src >> 16];
@@ -1066,7 +1132,9 @@ struct Ctx {
 
     __device__ void copy_traj(double *Xd, double *Ud, const double *Xs, const double *Us)
     {
+#pragma unroll 1
         for (int i = tid; i < N * n; i += T) Xd[i] = Xs[i];
+#pragma unroll 1
         for (int i = tid; i < (N - 1) * m; i += T) Ud[i] = Us[i];
         gsync<T>();
     }
@@ -1170,8 +1238,10 @@ struct Ctx {
 
     __device__ double gradient_todorov() const
     {
+#pragma unroll 1
         for (int k = tid; k < N - 1; k += T) {
             double mx = 0.0;
+#pragma unroll 1
             for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(dv[k * m + i]) / (fabs(U[k * m + i]) + 1.0));
             itm[k] = mx;
         }
@@ -1191,11 +1261,14 @@ struct Ctx {
             double s0 = P.noise_w1, s1 = P.noise_w1;
             if (P.noise_mode == 1) {
                 double mx = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(xo[i]));
                 s0 = s1 = mx * P.noise_w1;
             } else if (P.noise_mode == 2) {
                 double a = 0.0, b = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < n / 2; ++i) a += xo[i] * xo[i];
+#pragma unroll 1
                 for (int i = n / 2; i < n; ++i) b += xo[i] * xo[i];
                 s0 = sqrt(a) * P.noise_w1;
                 s1 = sqrt(b) * P.noise_w2;
@@ -1204,6 +1277,7 @@ struct Ctx {
             bc[4] = s1;
         }
         gsync<T>();
+#pragma unroll 1
         for (int i = tid; i < n; i += T) {
             double v = X[n + i];
             if (z) v += z[i] * bc[(P.noise_mode == 2 && i >= n / 2) ? 4 : 3];
@@ -1213,7 +1287,9 @@ struct Ctx {
             const int k0 = P.kidx[inst] + st + 1;
             if (ALL_SMEM || P.ref_in_smem) {  // the device track is padded with N copies of its last knot: one contiguous slice
                 const double *wx = P.trackX + (size_t)min(k0, P.Nt) * n, *wu = P.trackU + (size_t)min(k0, P.Nt - 1) * m;
+#pragma unroll 1
                 for (int i = tid; i < N * n; i += T) xr[i] = wx[i];
+#pragma unroll 1
                 for (int i = tid; i < (N - 1) * m; i += T) ur[i] = wu[i];
             } else {
                 xr = const_cast<double *>(P.trackX) + (size_t)min(k0, P.Nt) * n;
@@ -1222,6 +1298,7 @@ struct Ctx {
         }
         if (P.shift) {
             // in-place left shifts in chunks of T: all reads of a chunk precede its writes, later chunks are untouched
+#pragma unroll 1
             for (int base = 0; base < (N - 2) * m; base += T) {
                 const int i = base + tid;
                 double v = (i < (N - 2) * m) ? U[i + m] : 0.0;
@@ -1229,9 +1306,11 @@ struct Ctx {
                 if (i < (N - 2) * m) U[i] = v;
                 gsync<T>();
             }
+#pragma unroll 1
             for (int ci = 0; ci < ncon; ++ci) {
                 const int cnt = (cd[ci].k1 - cd[ci].k0 - 1) * cd[ci].p, p = cd[ci].p;
                 double *l = lam + cd[ci].dual_off;
+#pragma unroll 1
                 for (int base = 0; base < cnt; base += T) {
                     const int i = base + tid;
                     double v = (i < cnt) ? l[i + p] : 0.0;
@@ -1252,6 +1331,7 @@ struct Ctx {
         const long long cs = clock64();
         int iters = 0, outer_done = 0, status = ALTRO_UNSOLVED, trials = 0;
         double cmax = INFINITY, J = 0.0, pen_max = 0.0;
+#pragma unroll 1
         for (int outer = 1; outer <= o.iterations_outer; ++outer) {
             outer_done = outer;
             const bool last = (outer == o.iterations_outer) || ncon == 0;
@@ -1264,6 +1344,7 @@ struct Ctx {
             double J_prev = al_cost(X, U);
             J = J_prev;
             ph[0] += clock64() - c0;
+#pragma unroll 1
             for (int it = 0; it < o.iterations_inner; ++it) {
                 double dV1, dV2;
                 c0 = clock64();
@@ -1294,6 +1375,7 @@ struct Ctx {
             if (P.trace && tid == 0 && iters >= 1 && iters <= P.trace_rows)
                 P.trace[((size_t)inst * P.trace_rows + (iters - 1)) * TRACE_COLS + 9] = cmax;
             pen_max = 0.0;
+#pragma unroll 1
             for (int c = 0; c < ncon; ++c) pen_max = fmax(pen_max, mu[c]);
             if (cmax < o.constraint_tolerance) break;
             if (o.kickout_max_penalty && pen_max >= o.penalty_max) break;
@@ -1332,6 +1414,7 @@ struct Ctx {
         if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         load();
         const int steps = P.steps > 0 ? P.steps : 1;
+#pragma unroll 1
         for (int st = 0; st < steps; ++st) {
             if (P.steps > 0) {
                 set_step(st + 1);  // the window moves one knot forward with every transition
@@ -1339,15 +1422,19 @@ struct Ctx {
                 transition(st);
                 if (st > 0) {  // every solve! starts from reset penalties (and duals, if asked)
                     if (P.o.reset_duals)
+#pragma unroll 1
                         for (int i = tid; i < P.P; i += T) lam[i] = 0.0;
+#pragma unroll 1
                     for (int i = tid; i < MAX_CON; i += T) mu[i] = P.o.penalty_initial;
                     gsync<T>();
                 }
                 if (P.x0_log)
+#pragma unroll 1
                     for (int i = tid; i < n; i += T) P.x0_log[((size_t)st * P.B + inst) * n + i] = X[i];
             }
             solve_core(st);
             if (P.steps > 0 && P.u0_log)
+#pragma unroll 1
                 for (int i = tid; i < m; i += T) P.u0_log[((size_t)st * P.B + inst) * m + i] = U[i];
             if (tid == 0 && P.t_ns) {
                 long long t1v;
