@@ -46,7 +46,7 @@ struct ConDesc {
 // operand instead of re-deriving a chain of run-time products (11 % of all executed instructions before).
 struct Layout {
     int Qd, Qfd, Rd, sA, sB, sd, X, U, Xb, Ub, xr, ur, K, dv, lam, mu, ex, S, SA, Qxx, SB, Qux, T1, Quu, L, s, Qx, Qu,
-        t1, linv, red, bc, itm, cand, cd;  // cd: offset (in doubles) of the ConDesc array, followed by the gather tables
+        t1, linv, red, bc, itm, cand, Qi, cd;  // cd: offset (in doubles) of the ConDesc array, followed by the gather tables
     int bytes;                       // total dynamic shared memory
 };
 
@@ -65,6 +65,7 @@ __host__ __device__ constexpr Layout fixed_layout(int n, int m)
     l.S = q; q += n * n; l.SA = q; q += n * n; l.Qxx = q; q += n * n; l.SB = q; q += n * m; l.Qux = q; q += m * n;
     l.T1 = q; q += m * n; l.Quu = q; q += m * m; l.L = q; q += m * m;
     l.s = q; q += n; l.Qx = q; q += n; l.Qu = q; q += m; l.t1 = q; q += m; l.linv = q; q += m;
+    l.Qi = q; q += n + n * n + m + m * m;  // [Qx | Qxx | Qu | Quu] of the next knot: cost + AL expansion, gathered ahead
     l.mu = q; q += MAX_CON; l.bc = q; q += 24; l.red = q; q += 9;  // 8 broadcast slots + 16 speculative line-search results; 8 warps + 1
     l.X = q;
     return l;
@@ -184,42 +185,40 @@ __device__ __forceinline__ double gmax(double v, double *red)
 // out of line so that its register arrays get a register allocation of their own.  Lane i of warp 0 keeps row i
 // of the factor in registers and fetches the pivot row with shuffles (no shared-memory round trip per column);
 // the factor then goes to shared memory once and every right-hand side is substituted in registers by one thread.
-// Same fma / multiply sequence as the oracle's scalar loops.  Returns true if a pivot is not positive.
-template <int MM, int T>
-__device__ __noinline__ bool ldl_solve_medium(double *L, double *linv, double *flag, const double *Qux, const double *Qu,
-                                              double *Kk, double *dk_, int n)
+// Same fma / multiply sequence as the oracle's scalar loops.  Called by warp 0 only (the other warps prepare the
+// next knot meanwhile); returns true if a pivot is not positive.
+template <int MM>
+__device__ __noinline__ bool ldl_solve_medium(double *L, double *linv, const double *Qux, const double *Qu, double *Kk,
+                                              double *dk_, int n)
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lane = threadIdx.x & 31;
     bool bad = false;
-    if (warp == 0) {
-        double row[MM], rr[MM];
-        const int li = lane < MM ? lane : MM - 1;
+    double row[MM], rr[MM];
+    const int li = lane < MM ? lane : MM - 1;
 #pragma unroll
-        for (int j = 0; j < MM; ++j) row[j] = L[li * MM + j];
+    for (int j = 0; j < MM; ++j) row[j] = L[li * MM + j];
 #pragma unroll
-        for (int j = 0; j < MM; ++j) {
-            double acc = row[j];
+    for (int j = 0; j < MM; ++j) {
+        double acc = row[j];
 #pragma unroll
-            for (int l = 0; l < j; ++l) acc = fma(-row[l], __shfl_sync(0xffffffffu, row[l], j) * rr[l], acc);
-            row[j] = acc;
-            const double piv = __shfl_sync(0xffffffffu, acc, j);
-            if (!(piv > 0.0)) { bad = true; break; }
-            rr[j] = __drcp_rn(piv);
-        }
-        if (!bad && lane < MM) {
-#pragma unroll
-            for (int j = 0; j < MM; ++j) L[lane * MM + j] = row[j];
-        }
-        if (!bad && lane == 0) {
-#pragma unroll
-            for (int j = 0; j < MM; ++j) linv[j] = rr[j];
-        }
-        if (lane == 0) *flag = bad ? 1.0 : 0.0;
+        for (int l = 0; l < j; ++l) acc = fma(-row[l], __shfl_sync(0xffffffffu, row[l], j) * rr[l], acc);
+        row[j] = acc;
+        const double piv = __shfl_sync(0xffffffffu, acc, j);
+        if (!(piv > 0.0)) { bad = true; break; }
+        rr[j] = __drcp_rn(piv);
     }
-    gsync<T>();
-    bad = *flag != 0.0;
     if (bad) return true;
-    for (int c = tid; c <= n; c += T) {
+    if (lane < MM) {
+#pragma unroll
+        for (int j = 0; j < MM; ++j) L[lane * MM + j] = row[j];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < MM; ++j) linv[j] = rr[j];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int c = lane; c <= n; c += 32) {
         double *bp = (c < n) ? Kk + c : dk_;
         const double *src = (c < n) ? Qux + c : Qu;
         const int st = (c < n) ? n : 1;
@@ -228,17 +227,17 @@ __device__ __noinline__ bool ldl_solve_medium(double *L, double *linv, double *f
         for (int i = 0; i < MM; ++i) {
             double acc = -src[i * st];
 #pragma unroll
-            for (int l = 0; l < i; ++l) acc = fma(-L[i * MM + l], bb[l] * linv[l], acc);
+            for (int l = 0; l < i; ++l) acc = fma(-L[i * MM + l], bb[l] * rr[l], acc);
             bb[i] = acc;
         }
 #pragma unroll
-        for (int i = 0; i < MM; ++i) bb[i] = bb[i] * linv[i];
+        for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
 #pragma unroll
         for (int i = MM - 1; i >= 0; --i) {
             double acc2 = 0.0;
 #pragma unroll
             for (int l = MM - 1; l > i; --l) acc2 = fma(L[l * MM + i], bb[l], acc2);
-            bb[i] = fma(-linv[i], acc2, bb[i]);
+            bb[i] = fma(-rr[i], acc2, bb[i]);
         }
 #pragma unroll
         for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
@@ -257,7 +256,7 @@ struct Ctx {
     // shared memory
     double *Qd, *Qfd, *Rd, *sA, *sB, *sd;
     double *X, *U, *Xb, *Ub, *xr, *ur, *K, *dv, *lam, *mu, *ex;
-    double *S, *SA, *Qxx, *SB, *Qux, *T1, *Quu, *L, *s, *Qx, *Qu, *t1, *ldiag, *linv, *red, *bc, *itm;
+    double *S, *SA, *Qxx, *SB, *Qux, *T1, *Quu, *L, *s, *Qx, *Qu, *t1, *ldiag, *linv, *red, *bc, *itm, *Qi;
     int *gptr, *gsrc;  // gather lists: for every entry of [Qx | Qxx | Qu | Quu] the (block << 16 | offset) sources
     int NT;
     long long ph_exp = 0, ph_roll = 0, ph_cost = 0;  // profiling aid (P.phase)
@@ -283,12 +282,12 @@ struct Ctx {
             Qd = sm + f.Qd; Qfd = sm + f.Qfd; Rd = sm + f.Rd; sA = sm + f.sA; sB = sm + f.sB; sd = sm + f.sd;
             S = sm + f.S; SA = sm + f.SA; Qxx = sm + f.Qxx; SB = sm + f.SB; Qux = sm + f.Qux; T1 = sm + f.T1;
             Quu = sm + f.Quu; L = sm + f.L; s = sm + f.s; Qx = sm + f.Qx; Qu = sm + f.Qu; t1 = sm + f.t1;
-            linv = sm + f.linv; mu = sm + f.mu; bc = sm + f.bc; red = sm + f.red; X = sm + f.X;
+            linv = sm + f.linv; mu = sm + f.mu; bc = sm + f.bc; red = sm + f.red; Qi = sm + f.Qi; X = sm + f.X;
         } else {
             Qd = sm + l.Qd; Qfd = sm + l.Qfd; Rd = sm + l.Rd; sA = sm + l.sA; sB = sm + l.sB; sd = sm + l.sd;
             S = sm + l.S; SA = sm + l.SA; Qxx = sm + l.Qxx; SB = sm + l.SB; Qux = sm + l.Qux; T1 = sm + l.T1;
             Quu = sm + l.Quu; L = sm + l.L; s = sm + l.s; Qx = sm + l.Qx; Qu = sm + l.Qu; t1 = sm + l.t1;
-            linv = sm + l.linv; mu = sm + l.mu; bc = sm + l.bc; red = sm + l.red; X = sm + l.X;
+            linv = sm + l.linv; mu = sm + l.mu; bc = sm + l.bc; red = sm + l.red; Qi = sm + l.Qi; X = sm + l.X;
         }
         U = sm + l.U; Xb = sm + l.Xb; Ub = sm + l.Ub;
         K = sm + l.K; dv = sm + l.dv; lam = sm + l.lam;
@@ -725,6 +724,38 @@ struct Ctx {
         return base;
     }
 
+    // Everything knot k needs that does not depend on the cost-to-go: its LTV dynamics staged into shared memory and
+    // [Qx | Qxx | Qu | Quu] = cost expansion + AL expansion gathered into Qi.  Done by threads t0, t0+stride, ...:
+    // the warps that would idle while warp 0 factorises Quu of knot k+1 prepare knot k (backward_pass, P3).
+    __device__ __forceinline__ void prep_knot(int k, int t0, int stride)
+    {
+        if (!P.dyn_in_smem) {  // d_k is not needed by the backward pass
+            const double *gA = as_global(P.A) + dyn_index(k) * n * n;
+            const double *gB = as_global(P.Bm) + dyn_index(k) * n * m;
+#pragma unroll 2
+            for (int i = t0; i < n * n; i += stride) sA[i] = gA[i];
+#pragma unroll 2
+            for (int i = t0; i < n * m; i += stride) sB[i] = gB[i];
+        }
+        const int oQxx = n, oQu = n + n * n, oQuu = n + n * n + m;
+#pragma unroll 1
+        for (int t = t0; t < NT; t += stride) {
+            double base;
+            if (t < oQxx) base = P.dt * Qd[t] * (X[k * n + t] - xr[k * n + t]);
+            else if (t < oQu) {
+                const int e = t - oQxx, i = e / n, j = e - i * n;
+                base = (i == j) ? P.dt * Qd[i] : 0.0;
+            } else if (t < oQuu) {
+                const int i = t - oQu;
+                base = P.dt * Rd[i] * (U[k * m + i] - ur[k * m + i]);
+            } else {
+                const int e = t - oQuu, i = e / m, j = e - i * m;
+                base = (i == j) ? P.dt * Rd[i] : 0.0;
+            }
+            Qi[t] = gather(t, k, base);
+        }
+    }
+
     // ---------------------------------------------------------------- backward pass (A.7)
     __device__ void reg_increase(double &rho, double &drho) const
     {
@@ -780,18 +811,12 @@ struct Ctx {
                     S[e] = gather(t, N - 1, (i == j) ? Qfd[i] : 0.0);
                 }
             }
+            prep_knot(N - 2, tid, T);
             gsync<T>();
             for (int k = N - 2; k >= 0; --k) {
                 long long tq = clock64(), tq2;
 #define ALTRO_TICK(slot) do { tq2 = clock64(); bpc[slot] += tq2 - tq; tq = tq2; } while (0)
-                if (!P.dyn_in_smem) {  // LTV: stage A_k, B_k into shared memory (coalesced), d_k is not needed here
-                    const double *gA = P.A + dyn_index(k) * n * n;
-                    const double *gB = P.Bm + dyn_index(k) * n * m;
-                    for (int i = tid; i < n * n; i += T) sA[i] = gA[i];
-                    for (int i = tid; i < n * m; i += T) sB[i] = gB[i];
-                    gsync<T>();
-                }
-                // P1: SA = S A, SB = S B (tensor tiles); cost + AL expansion gathered into Qx, Qxx, Qu, Quu
+                // P1: SA = S A, SB = S B (tensor tiles); A_k, B_k and Qi were prepared during the previous knot
                 for (int t = warp; t < tn * (tn + tm); t += NW) {
                     const int r0 = (t / (tn + tm)) << 3, ct = t % (tn + tm);
                     const int i = r0 + fr;
@@ -816,19 +841,6 @@ struct Ctx {
                         }
                     }
                 }
-                for (int t = tid; t < NT; t += T) {
-                    if (t < oQxx) Qx[t] = gather(t, k, P.dt * Qd[t] * (X[k * n + t] - xr[k * n + t]));
-                    else if (t < oQu) {
-                        const int e = t - oQxx, i = e / n, j = e - i * n;
-                        Qxx[e] = gather(t, k, (i == j) ? P.dt * Qd[i] : 0.0);
-                    } else if (t < oQuu) {
-                        const int i = t - oQu;
-                        Qu[i] = gather(t, k, P.dt * Rd[i] * (U[k * m + i] - ur[k * m + i]));
-                    } else {
-                        const int e = t - oQuu, i = e / m, j = e - i * m;
-                        Quu[e] = gather(t, k, (i == j) ? P.dt * Rd[i] : 0.0);
-                    }
-                }
                 gsync<T>();
                 ALTRO_TICK(0);
                 // P2: [Qxx | Qx] += A'[SA | s],  Qux = B'SA,  [Quu | Qu] += B'[SB | s]   (chains start from the
@@ -838,8 +850,8 @@ struct Ctx {
                     if (t < nt_xx) {
                         const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
                         const int i = r0 + fr, j = c0 + fc;
-                        double d0 = (i < n) ? (j < n ? Qxx[i * n + j] : (j == n ? Qx[i] : 0.0)) : 0.0;
-                        double d1 = (i < n) ? (j + 1 < n ? Qxx[i * n + j + 1] : (j + 1 == n ? Qx[i] : 0.0)) : 0.0;
+                        double d0 = (i < n) ? (j < n ? Qi[oQxx + i * n + j] : (j == n ? Qi[i] : 0.0)) : 0.0;
+                        double d1 = (i < n) ? (j + 1 < n ? Qi[oQxx + i * n + j + 1] : (j + 1 == n ? Qi[i] : 0.0)) : 0.0;
                         mma_chain(d0, d1, n,
                                   [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? A[l * n + ii] : 0.0; },
                                   [&](int l, int jj) {
@@ -865,8 +877,8 @@ struct Ctx {
                     } else {
                         const int u = t - nt_xx - nt_ux, r0 = (u / tm1) << 3, c0 = (u % tm1) << 3;
                         const int i = r0 + fr, j = c0 + fc;
-                        double d0 = (i < m) ? (j < m ? Quu[i * m + j] : (j == m ? Qu[i] : 0.0)) : 0.0;
-                        double d1 = (i < m) ? (j + 1 < m ? Quu[i * m + j + 1] : (j + 1 == m ? Qu[i] : 0.0)) : 0.0;
+                        double d0 = (i < m) ? (j < m ? Qi[oQuu + i * m + j] : (j == m ? Qi[oQu + i] : 0.0)) : 0.0;
+                        double d1 = (i < m) ? (j + 1 < m ? Qi[oQuu + i * m + j + 1] : (j + 1 == m ? Qi[oQu + i] : 0.0)) : 0.0;
                         mma_chain(d0, d1, n,
                                   [&](int ii, int l) { ii += r0; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
                                   [&](int l, int jj) {
@@ -890,52 +902,65 @@ struct Ctx {
                 //     x_i = z_i - r_i sum_{q>i} X[q][i] x_q (q descending).  One right-hand side per thread.
                 bool bad = false;
                 double *Kk = K + k * m * n, *dk_ = dv + k * m;
-                if (NU > 0 && NU <= 4) {
-                    // tiny control dimension: every lane factorises in registers (no barrier, no broadcast),
-                    // lanes c <= n then solve their own right-hand side
-                    constexpr int MM = NU > 0 ? NU : 1;
-                    double Xr[MM * MM], rr[MM];
+                if (NU > 0 && NU <= 16) {
+                    // Small / medium control dimension: warp 0 factorises and substitutes in registers while the other
+                    // warps (if any) prepare the next knot -- its dynamics and gathered expansion do not depend on
+                    // the cost-to-go, so the gather and the global-memory latency hide behind the factorisation.
+                    if (warp == 0) {
+                        if (NU <= 4) {
+                            constexpr int MM = (NU > 0 && NU <= 4) ? NU : 1;
+                            double Xr[MM * MM], rr[MM];
 #pragma unroll
-                    for (int j = 0; j < MM; ++j) {
+                            for (int j = 0; j < MM; ++j) {
 #pragma unroll
-                        for (int i = j; i < MM; ++i) {
-                            double acc = L[i * MM + j];
+                                for (int i = j; i < MM; ++i) {
+                                    double acc = L[i * MM + j];
 #pragma unroll
-                            for (int l = 0; l < j; ++l) acc = fma(-Xr[i * MM + l], Xr[j * MM + l] * rr[l], acc);
-                            Xr[i * MM + j] = acc;
-                        }
-                        if (!(Xr[j * MM + j] > 0.0)) { bad = true; break; }
-                        rr[j] = __drcp_rn(Xr[j * MM + j]);
-                    }
-                    if (!bad) {
-                        for (int c = tid; c <= n; c += T) {
-                            double *bp = (c < n) ? Kk + c : dk_;
-                            const double *src = (c < n) ? Qux + c : Qu;
-                            const int st = (c < n) ? n : 1;
-                            double bb[MM];
-#pragma unroll
-                            for (int i = 0; i < MM; ++i) {
-                                double acc = -src[i * st];
-#pragma unroll
-                                for (int l = 0; l < i; ++l) acc = fma(-Xr[i * MM + l], bb[l] * rr[l], acc);
-                                bb[i] = acc;
+                                    for (int l = 0; l < j; ++l) acc = fma(-Xr[i * MM + l], Xr[j * MM + l] * rr[l], acc);
+                                    Xr[i * MM + j] = acc;
+                                }
+                                if (!(Xr[j * MM + j] > 0.0)) { bad = true; break; }
+                                rr[j] = __drcp_rn(Xr[j * MM + j]);
                             }
+                            if (!bad) {
+#pragma unroll 1
+                                for (int c = lane; c <= n; c += 32) {
+                                    double *bp = (c < n) ? Kk + c : dk_;
+                                    const double *src = (c < n) ? Qux + c : Qu;
+                                    const int st = (c < n) ? n : 1;
+                                    double bb[MM];
 #pragma unroll
-                            for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
+                                    for (int i = 0; i < MM; ++i) {
+                                        double acc = -src[i * st];
 #pragma unroll
-                            for (int i = MM - 1; i >= 0; --i) {
-                                double acc2 = 0.0;
+                                        for (int l = 0; l < i; ++l) acc = fma(-Xr[i * MM + l], bb[l] * rr[l], acc);
+                                        bb[i] = acc;
+                                    }
 #pragma unroll
-                                for (int l = MM - 1; l > i; --l) acc2 = fma(Xr[l * MM + i], bb[l], acc2);
-                                bb[i] = fma(-rr[i], acc2, bb[i]);
+                                    for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
+#pragma unroll
+                                    for (int i = MM - 1; i >= 0; --i) {
+                                        double acc2 = 0.0;
+#pragma unroll
+                                        for (int l = MM - 1; l > i; --l) acc2 = fma(Xr[l * MM + i], bb[l], acc2);
+                                        bb[i] = fma(-rr[i], acc2, bb[i]);
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
+                                }
                             }
-#pragma unroll
-                            for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
+                        } else {
+                            bad = ldl_solve_medium<(NU > 4 && NU <= 16) ? NU : 5>(L, linv, Qux, Qu, Kk, dk_, n);
                         }
+                        if (T > 32 && lane == 0) bc[5] = bad ? 1.0 : 0.0;
+                        if (T == 32 && !bad && k > 0) prep_knot(k - 1, tid, T);
+                    } else if (k > 0) {
+                        prep_knot(k - 1, tid - 32, T - 32);
                     }
-                    ALTRO_TICK(3);
-                } else if (NU > 4 && NU <= 16) {
-                    bad = ldl_solve_medium<(NU > 4 && NU <= 16) ? NU : 5, T>(L, linv, bc + 5, Qux, Qu, Kk, dk_, n);
+                    if (T > 32) {
+                        gsync<T>();
+                        bad = bc[5] != 0.0;
+                    }
                     ALTRO_TICK(3);
                 } else {
                     if (m <= 32) {  // warp 0 alone, one lane per row, one __syncwarp per column
@@ -991,6 +1016,7 @@ struct Ctx {
                             }
                         }
                     }
+                    if (!bad && k > 0) prep_knot(k - 1, tid, T);
                 }
                 if (bad) { restart = true; break; }
                 gsync<T>();
