@@ -489,11 +489,10 @@ struct Ctx {
     {
         const int items = N * (1 + ncon);
 #pragma unroll 1
-        for (int k = tid; k < N; k += T) itm[k] = stage_cost(k, Xc, Uc);
-#pragma unroll 1
-        for (int j = 0; j < ncon; ++j)
-#pragma unroll 1
-            for (int k = tid; k < N; k += T) itm[(j + 1) * N + k] = con_cost(j, k, Xc, Uc);
+        for (int it = tid; it < items; it += T) {  // piece-major: neighbouring lanes share the piece (no divergence)
+            const int j = it / N, k = it - j * N;
+            itm[it] = (j == 0) ? stage_cost(k, Xc, Uc) : con_cost(j - 1, k, Xc, Uc);
+        }
         gsync<T>();
         return csum<T>(itm, items, bc, tid);
     }
@@ -511,10 +510,10 @@ struct Ctx {
     {
         double v = 0.0;
 #pragma unroll 1
-        for (int ci = 0; ci < ncon; ++ci) {
+        for (int it = tid; it < ncon * N; it += T) {  // (block, knot) work items, block-major
+            const int ci = it / N, k = it - ci * N;
             const ConDesc &c = cd[ci];
-#pragma unroll 1
-            for (int k = c.k0 + tid; k < c.k1; k += T) {
+            if (k >= c.k0 && k < c.k1) {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
@@ -554,11 +553,11 @@ struct Ctx {
     __device__ void dual_update()
     {
 #pragma unroll 1
-        for (int ci = 0; ci < ncon; ++ci) {
+        for (int it = tid; it < ncon * N; it += T) {  // (block, knot) work items, block-major
+            const int ci = it / N, k = it - ci * N;
             const ConDesc &c = cd[ci];
             const double mu_c = mu[ci];
-#pragma unroll 1
-            for (int k = c.k0 + tid; k < c.k1; k += T) {
+            if (k >= c.k0 && k < c.k1) {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
@@ -602,12 +601,12 @@ struct Ctx {
     __device__ void expand_constraints()
     {
 #pragma unroll 1
-        for (int ci = 0; ci < ncon; ++ci) {
+        for (int it = tid; it < ncon * N; it += T) {  // (block, knot) work items, block-major
+            const int ci = it / N, k = it - ci * N;
             const ConDesc &c = cd[ci];
             const double mu_c = mu[ci];
             const int w = c.w, p = c.p;
-#pragma unroll 1
-            for (int k = c.k0 + tid; k < c.k1; k += T) {
+            if (k >= c.k0 && k < c.k1) {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * p * w, *h = as_global(c.h) + di * p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
