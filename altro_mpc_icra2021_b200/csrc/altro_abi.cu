@@ -67,7 +67,7 @@ struct altro_handle_s {
     ConDesc *con_dev = nullptr;
     int *itab_dev = nullptr;
     double *ex_glob = nullptr;
-    int P = 0, EX = 0, ITAB = 0;
+    int P = 0, EX = 0, ITAB = 0, NSRC = 0, NTL = 0;
     bool finalized = false, have_dyn = false, have_cost = false, have_ref = false, have_x0 = false;
     // MPC track
     double *trackX = nullptr, *trackU = nullptr, *noise = nullptr, *noise_bank = nullptr;
@@ -302,10 +302,27 @@ int finalize(altro_handle_t h)
     }
     h->P = P;
     h->EX = EX;
-    {  // CSR gather table: gptr[NT+1] then gsrc[]; per target the sources stay in ascending block order
-        std::vector<int> itab(NT + 1, 0);
-        for (int t = 0; t < NT; ++t) itab[t + 1] = itab[t] + (int)srcs[t].size();
-        for (int t = 0; t < NT; ++t) itab.insert(itab.end(), srcs[t].begin(), srcs[t].end());
+    {  // Gather table: one 16-byte record {k0, k1, offset at knot 0, stride per knot} per source, in CSR order (per
+       // target the sources stay in ascending block order), then gptr[NT+1], then the list of targets that are
+       // refreshed at every knot: the two vectors and the matrix entries at least one block touches.
+        std::vector<int> itab;
+        std::vector<int> gptr(NT + 1, 0), tl;
+        for (int t = 0; t < NT; ++t) {
+            gptr[t + 1] = gptr[t] + (int)srcs[t].size();
+            for (int src : srcs[t]) {
+                const ConDesc &c = cd[src >> 16];
+                itab.push_back(c.k0);
+                itab.push_back(c.k1);
+                itab.push_back(c.ex_off - c.k0 * c.ex_stride + (src & 0xffff));
+                itab.push_back(c.ex_stride);
+            }
+            const bool vec = t < n || (t >= n + n * n && t < n + n * n + m);
+            if (vec || !srcs[t].empty()) tl.push_back(t);
+        }
+        h->NSRC = gptr[NT];
+        h->NTL = (int)tl.size();
+        itab.insert(itab.end(), gptr.begin(), gptr.end());
+        itab.insert(itab.end(), tl.begin(), tl.end());
         h->ITAB = (int)itab.size();
         CK(h, dalloc(&h->itab_dev, itab.size()));
         CK(h, cudaMemcpy(h->itab_dev, itab.data(), itab.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -810,7 +827,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
 {
     Params P;
     memset(&P, 0, sizeof(P));
-    P.n = h->n; P.m = h->m; P.N = h->N; P.B = h->B; P.P = h->P; P.ncon = (int)h->cons.size(); P.EX = h->EX; P.ITAB = h->ITAB;
+    P.n = h->n; P.m = h->m; P.N = h->N; P.B = h->B; P.P = h->P; P.ncon = (int)h->cons.size(); P.EX = h->EX; P.ITAB = h->ITAB; P.NSRC = h->NSRC; P.NTL = h->NTL;
     P.inst_offset = 0;
     P.dt = h->dt;
     P.dyn_per_knot = h->dyn_per_knot; P.dyn_per_instance = h->dyn_per_instance; P.dyn_in_smem = h->dyn_in_smem; P.ref_in_smem = h->ref_in_smem;

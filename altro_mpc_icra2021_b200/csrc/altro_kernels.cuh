@@ -26,7 +26,7 @@ constexpr int DENSE_W = 8;   // index-set width of a dense block
 constexpr int TRACE_COLS = 10;  // outer, iter, J, dJ, grad, rho, dV1, dV2, ls trials so far, c_max (NaN inside an outer)
 
 // One affine conic block c = G z[inds] + h (device view).
-struct ConDesc {
+struct alignas(16) ConDesc {
     int sense, side, k0, k1, p, w;
     int per_knot, per_instance;
     int rowsparse;  // every row of G has <= 1 nonzero (bounds): value = h[r] + rs_coef[r] * z[inds[rs_col[r]]]
@@ -86,6 +86,7 @@ __host__ __device__ inline Layout make_layout(int n, int m, int N, int P, int nc
     l.itm = take(N * (1 + ncon));
     // speculative line search: one extra (Xb, Ub, itm) set per additional warp
     l.cand = take(spec_sets * (N * n + (N - 1) * m + N * (1 + ncon)));
+    q += q & 1;  // the descriptors and the gather records behind them are read as 16-byte words
     l.cd = q;
     size_t b = (size_t)q * sizeof(double) + (size_t)(ncon > 0 ? ncon : 1) * sizeof(ConDesc) + (size_t)ITAB * sizeof(int);
     l.bytes = (int)((b + 15) & ~(size_t)15);
@@ -94,6 +95,7 @@ __host__ __device__ inline Layout make_layout(int n, int m, int N, int P, int nc
 
 struct Params {
     int n, m, N, B, P, ncon, EX, ITAB;
+    int NSRC, NTL;  // gather table: NSRC source records, NTL targets refreshed at every knot (see Ctx::gather)
     int inst_offset;
     double dt;
     int dyn_per_knot, dyn_per_instance, dyn_in_smem, ref_in_smem;
@@ -257,7 +259,8 @@ struct Ctx {
     double *Qd, *Qfd, *Rd, *sA, *sB, *sd;
     double *X, *U, *Xb, *Ub, *xr, *ur, *K, *dv, *lam, *mu, *ex;
     double *S, *SA, *Qxx, *SB, *Qux, *T1, *Quu, *L, *s, *Qx, *Qu, *t1, *ldiag, *linv, *red, *bc, *itm, *Qi;
-    int *gptr, *gsrc;  // gather lists: for every entry of [Qx | Qxx | Qu | Quu] the (block << 16 | offset) sources
+    int4 *grec;
+    int *gptr, *gtl;  // gather lists: for every entry of [Qx | Qxx | Qu | Quu] the (block << 16 | offset) sources
     int NT;
     long long ph_exp = 0, ph_roll = 0, ph_cost = 0;  // profiling aid (P.phase)
     long long bpc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -306,8 +309,9 @@ struct Ctx {
         ldiag = nullptr; itm = sm + l.itm; specr = bc + 8;
         cd = reinterpret_cast<ConDesc *>(sm + l.cd);
         NT = n + n * n + m + m * m;
-        gptr = reinterpret_cast<int *>(cd + (ncon > 0 ? ncon : 1));
-        gsrc = gptr + NT + 1;
+        grec = reinterpret_cast<int4 *>(cd + (ncon > 0 ? ncon : 1));
+        gptr = reinterpret_cast<int *>(grec + P.NSRC);
+        gtl = gptr + NT + 1;
         dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_sched ? (size_t)P.dyn_slots : (P.dyn_per_knot ? (size_t)(N - 1) : 1)) : 0;
         dyn_k = P.dyn_per_knot ? 1 : 0;
         sched = nullptr;
@@ -388,7 +392,14 @@ struct Ctx {
 #pragma unroll 1
         for (int i = tid; i < words; i += T) dst[i] = src[i];
 #pragma unroll 1
-        for (int i = tid; i < P.ITAB; i += T) gptr[i] = P.itab[i];
+        for (int i = tid; i < P.ITAB; i += T) reinterpret_cast<int *>(grec)[i] = P.itab[i];
+#pragma unroll 1
+        for (int t = tid; t < NT; t += T) {  // matrix entries no block touches keep the cost Hessian for the whole launch
+            double base = 0.0;
+            if (t >= n && t < n + n * n) { const int e = t - n, i = e / n, j = e - i * n; base = (i == j) ? P.dt * P.Q[i] : 0.0; }
+            else if (t >= n + n * n + m) { const int e = t - (n + n * n + m), i = e / m, j = e - i * m; base = (i == j) ? P.dt * P.R[i] : 0.0; }
+            Qi[t] = base;
+        }
         gsync<T>();
     }
 
@@ -716,9 +727,8 @@ struct Ctx {
     {
 #pragma unroll 1
         for (int q = gptr[t]; q < gptr[t + 1]; ++q) {
-            const int src = gsrc[q];
-            const ConDesc &c = cd[src >> 16];
-            if (k >= c.k0 && k < c.k1) base += ex[c.ex_off + (k - c.k0) * c.ex_stride + (src & 0xffff)];
+            const int4 r = grec[q];  // {k0, k1, offset of the entry at knot 0, stride per knot}
+            if (k >= r.x && k < r.y) base += ex[r.z + k * r.w];
         }
         return base;
     }
@@ -738,7 +748,8 @@ struct Ctx {
         }
         const int oQxx = n, oQu = n + n * n, oQuu = n + n * n + m;
 #pragma unroll 1
-        for (int t = t0; t < NT; t += stride) {
+        for (int q = t0; q < P.NTL; q += stride) {  // the vectors and the matrix entries some block touches
+            const int t = gtl[q];
             double base;
             if (t < oQxx) base = P.dt * Qd[t] * (X[k * n + t] - xr[k * n + t]);
             else if (t < oQu) {
