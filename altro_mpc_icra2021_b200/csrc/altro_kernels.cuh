@@ -50,6 +50,9 @@ struct Layout {
     int bytes;                       // total dynamic shared memory
 };
 
+#ifndef ALTRO_T128_CTAS
+#define ALTRO_T128_CTAS 4  // resident CTAs per SM the 128-thread small-dimension kernels are register-capped for
+#endif
 #ifndef ALTRO_FIXED_ALL_SMEM
 #define ALTRO_FIXED_ALL_SMEM 1
 #endif
@@ -967,11 +970,12 @@ struct Ctx {
                     } else if (k > 0) {
                         prep_knot(k - 1, tid - 32, T - 32);
                     }
+                    ALTRO_TICK(1);  // warp 0: its own factorisation + substitution
                     if (T > 32) {
                         gsync<T>();
                         bad = bc[5] != 0.0;
                     }
-                    ALTRO_TICK(3);
+                    ALTRO_TICK(3);  // wait for the warps that prepared the next knot
                 } else {
                     if (m <= 32) {  // warp 0 alone, one lane per row, one __syncwarp per column
                         if (warp == 0) {
@@ -1489,7 +1493,7 @@ template <int NX, int NU, int T>
 // (measured, scripts/dev_perf.py): quadruped (12,12) is fastest with the whole register file at 4 CTAs/SM; the other
 // 12-dimensional and run-time sized problems with a 168-register cap (6 CTAs/SM at T = 64).
 __global__ void __launch_bounds__(T, ((NX == 12 && NU == 12) ? (256 / T > 0 ? 256 / T : 1)
-                                      : (NX >= 12 || NX == 0) ? (384 / T > 0 ? 384 / T : 1) : 512 / T)) altro_solve_kernel(const __grid_constant__ Params P)
+                                      : (NX >= 12 || NX == 0) ? (384 / T > 0 ? 384 / T : 1) : (T == 128 ? ALTRO_T128_CTAS : 512 / T))) altro_solve_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<NX, NU, T> ctx(P, smem_raw);

@@ -26,7 +26,7 @@ if wl.qstate is None:
           f"per-instance total ms mean {tot_i.mean()/1e3:.2f} max {tot_i.max()/1e3:.2f}; iters {it.mean():.2f} ls {ls.mean():.2f}")
     if os.environ.get("ALTRO_B200_PHASE_DETAIL"):
         nit = ph[:, 7].sum()
-        print("bp sub-phase cycles per iteration:", {nm: int(ph[:, i].sum() / nit) for i, nm in enumerate(["P1 SA/SB+init", "scatter", "P2 Q", "P3 chol", "P4 solve", "P5 T1", "P6 S"])})
+        print("bp sub-phase cycles per iteration:", {nm: int(ph[:, i].sum() / nit) for i, nm in enumerate(["P1 SA/SB", "P3 warp0 LDL+solve", "P2 Q", "P3 wait prep", "P4 solve", "P5 T1", "P6 S"])})
         sys.exit(0)
     tot = ph[:, 3].sum()
     names = ["init rollout+cost", "backward(+expand)", "forward", "whole", "expand", "ls rollouts", "ls costs"]
