@@ -431,12 +431,26 @@ struct Ctx {
 
     // ---------------------------------------------------------------- constraint values
     // Row r of block c at knot k evaluated on z (x_k or u_k): TO.evaluate.
+    // The block's slice of z, fetched once per (block, knot) item for narrow dense blocks (cones, pyramids: w <= ZW) so
+    // that the rows are pure G loads + fma instead of a dependent index -> value load chain per term.
+    static constexpr int ZW = 4;
+    __device__ __forceinline__ void load_zl(const ConDesc &c, const double *z, double (&zl)[ZW]) const
+    {
+#pragma unroll
+        for (int j = 0; j < ZW; ++j) zl[j] = (!c.rowsparse && j < c.w) ? z[c.inds[j]] : 0.0;
+    }
     __device__ __forceinline__ double row_value(const ConDesc &c, const double *G, const double *h, const double *z,
-                                                int r) const
+                                                const double (&zl)[ZW], int r) const
     {
         if (c.rowsparse) return fma(as_global(c.rs_coef)[r], z[c.inds[as_global(c.rs_col)[r]]], h[r]);
         double acc = h[r];
         const double *g = G + r * c.w;
+        if (c.w <= ZW) {  // same ascending-index fma chain, operands already in registers
+#pragma unroll
+            for (int j = 0; j < ZW; ++j)
+                if (j < c.w) acc = fma(g[j], zl[j], acc);
+            return acc;
+        }
 #pragma unroll 1
         for (int j = 0; j < c.w; ++j) acc = fma(g[j], z[c.inds[j]], acc);
         return acc;
@@ -450,19 +464,21 @@ struct Ctx {
         const size_t di = con_idx(c, k);
         const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
         const double *z = c.side == ALTRO_STATE ? Xc + k * n : Uc + k * m;
+        double zl[ZW];
+        load_zl(c, z, zl);
         const double *l = lam + c.dual_off + (k - c.k0) * c.p;
         const double mu_c = mu[ci];
         double J = 0.0;
         if (c.sense == ALTRO_EQUALITY) {
 #pragma unroll 1
             for (int r = 0; r < c.p; ++r) {
-                double v = row_value(c, G, h, z, r);
+                double v = row_value(c, G, h, z, zl, r);
                 J += l[r] * v + 0.5 * mu_c * v * v;
             }
         } else if (c.sense == ALTRO_INEQUALITY) {
 #pragma unroll 1
             for (int r = 0; r < c.p; ++r) {
-                double v = row_value(c, G, h, z, r);
+                double v = row_value(c, G, h, z, zl, r);
                 bool act = (v >= 0.0) || (l[r] > 0.0);
                 J += l[r] * v + (act ? 0.5 * mu_c * v * v : 0.0);
             }
@@ -470,7 +486,7 @@ struct Ctx {
             double a2 = 0.0, t = 0.0, nl = 0.0;
 #pragma unroll 1
             for (int r = 0; r < c.p; ++r) {
-                double lb = l[r] - mu_c * row_value(c, G, h, z, r);
+                double lb = l[r] - mu_c * row_value(c, G, h, z, zl, r);
                 nl += l[r] * l[r];
                 if (r < c.p - 1) a2 += lb * lb;
                 else t = lb;
@@ -531,17 +547,19 @@ struct Ctx {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
+                double zl[ZW];
+                load_zl(c, z, zl);
                 if (c.sense == ALTRO_EQUALITY) {
 #pragma unroll 1
-                    for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
+                    for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, zl, r)));
                 } else if (c.sense == ALTRO_INEQUALITY) {
 #pragma unroll 1
-                    for (int r = 0; r < c.p; ++r) v = fmax(v, row_value(c, G, h, z, r));
+                    for (int r = 0; r < c.p; ++r) v = fmax(v, row_value(c, G, h, z, zl, r));
                 } else {
                     double a2 = 0.0, t = 0.0;
 #pragma unroll 1
                     for (int r = 0; r < c.p; ++r) {
-                        double cv = row_value(c, G, h, z, r);
+                        double cv = row_value(c, G, h, z, zl, r);
                         if (r < c.p - 1) a2 += cv * cv;
                         else t = cv;
                     }
@@ -550,11 +568,11 @@ struct Ctx {
                         v = fmax(v, a - t);
                     } else if (a <= -t) {  // projection is 0: distance = |c|_inf
 #pragma unroll 1
-                        for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, r)));
+                        for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, z, zl, r)));
                     } else if (a > t) {  // c - Pi(c) = ((1-cf) v, t - cf a)
                         double cf = 0.5 * (1.0 + t / a);
 #pragma unroll 1
-                        for (int r = 0; r < c.p - 1; ++r) v = fmax(v, fabs((1.0 - cf) * row_value(c, G, h, z, r)));
+                        for (int r = 0; r < c.p - 1; ++r) v = fmax(v, fabs((1.0 - cf) * row_value(c, G, h, z, zl, r)));
                         v = fmax(v, fabs(t - cf * a));
                     }
                 }
@@ -575,20 +593,22 @@ struct Ctx {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * c.p * c.w, *h = as_global(c.h) + di * c.p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
+                double zl[ZW];
+                load_zl(c, z, zl);
                 double *l = lam + c.dual_off + (k - c.k0) * c.p;
                 if (c.sense == ALTRO_EQUALITY) {
 #pragma unroll 1
                     for (int r = 0; r < c.p; ++r)
-                        l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, r), -P.o.dual_max), P.o.dual_max);
+                        l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, zl, r), -P.o.dual_max), P.o.dual_max);
                 } else if (c.sense == ALTRO_INEQUALITY) {
 #pragma unroll 1
                     for (int r = 0; r < c.p; ++r)
-                        l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, r), 0.0), P.o.dual_max);
+                        l[r] = fmin(fmax(l[r] + mu_c * row_value(c, G, h, z, zl, r), 0.0), P.o.dual_max);
                 } else {
                     double a2 = 0.0, t = 0.0;
 #pragma unroll 1
                     for (int r = 0; r < c.p; ++r) {
-                        double lb = l[r] - mu_c * row_value(c, G, h, z, r);
+                        double lb = l[r] - mu_c * row_value(c, G, h, z, zl, r);
                         l[r] = lb;
                         if (r < c.p - 1) a2 += lb * lb;
                         else t = lb;
@@ -624,6 +644,8 @@ struct Ctx {
                 const size_t di = con_idx(c, k);
                 const double *G = as_global(c.G) + di * p * w, *h = as_global(c.h) + di * p;
                 const double *z = c.side == ALTRO_STATE ? X + k * n : U + k * m;
+                double zl[ZW];
+                load_zl(c, z, zl);
                 const double *l = lam + c.dual_off + (k - c.k0) * p;
                 double *g = ex + c.ex_off + (k - c.k0) * c.ex_stride;
                 double *H = g + w;
@@ -632,7 +654,7 @@ struct Ctx {
                     for (int j = 0; j < 2 * w; ++j) g[j] = 0.0;
 #pragma unroll 1
                     for (int r = 0; r < p; ++r) {
-                        double v = row_value(c, G, h, z, r), cf = as_global(c.rs_coef)[r];
+                        double v = row_value(c, G, h, z, zl, r), cf = as_global(c.rs_coef)[r];
                         bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l[r] > 0.0);
                         int col = as_global(c.rs_col)[r];
                         g[col] += cf * (l[r] + (act ? mu_c * v : 0.0));
@@ -642,7 +664,7 @@ struct Ctx {
                     double y[PMAX], D[PMAX];
 #pragma unroll 1
                     for (int r = 0; r < p; ++r) {
-                        double v = row_value(c, G, h, z, r);
+                        double v = row_value(c, G, h, z, zl, r);
                         bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l[r] > 0.0);
                         y[r] = l[r] + (act ? mu_c * v : 0.0);
                         D[r] = act ? mu_c : 0.0;
@@ -669,7 +691,7 @@ struct Ctx {
                     double a2 = 0.0;
 #pragma unroll 1
                     for (int r = 0; r < p; ++r) {
-                        lb[r] = l[r] - mu_c * row_value(c, G, h, z, r);
+                        lb[r] = l[r] - mu_c * row_value(c, G, h, z, zl, r);
                         if (r < p - 1) a2 += lb[r] * lb[r];
                     }
                     const double t = lb[p - 1], a = sqrt(a2);
@@ -827,8 +849,16 @@ struct Ctx {
             prep_knot(N - 2, tid, T);
             gsync<T>();
             for (int k = N - 2; k >= 0; --k) {
+#ifdef ALTRO_PHASE_TIMERS
                 long long tq = clock64(), tq2;
+#else
+                long long tq = 0, tq2 = 0;
+#endif
+#ifdef ALTRO_PHASE_TIMERS  // development builds only (make EXTRA=-DALTRO_PHASE_TIMERS): 7 clock reads per knot
 #define ALTRO_TICK(slot) do { tq2 = clock64(); bpc[slot] += tq2 - tq; tq = tq2; } while (0)
+#else
+#define ALTRO_TICK(slot) do { (void)tq; (void)tq2; } while (0)
+#endif
                 // P1: SA = S A, SB = S B (tensor tiles); A_k, B_k and Qi were prepared during the previous knot
                 for (int t = warp; t < tn * (tn + tm); t += NW) {
                     const int r0 = (t / (tn + tm)) << 3, ct = t % (tn + tm);
