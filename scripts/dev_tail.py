@@ -31,3 +31,4 @@ for i in order[:8]:
 ok = st == st.ravel()[np.argmin(t.ravel())]
 print("share of CTA time in solves whose status differs from the fastest solve's:", t[~ok].sum() / t.sum(), "count", (~ok).sum())
 print("time share by iteration count bucket:", {b: round(float(t[(it >= lo) & (it < hi)].sum() / t.sum()), 3) for b, (lo, hi) in {"<=3": (0, 4), "4-10": (4, 11), "11-50": (11, 51), ">50": (51, 10**9)}.items()})
+np.savez_compressed(os.path.join("gpurun_out", f"tail_{name}.npz"), t_us=t, it=it)
