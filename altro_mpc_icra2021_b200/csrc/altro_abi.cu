@@ -897,6 +897,15 @@ int altro_mpc_run(altro_handle_t h, int steps, int shift)
     return launch_solve(h, steps, shift);
 }
 
+int altro_reserve_steps(altro_handle_t h, int steps)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (steps < 1) return fail(h, ALTRO_ERR_INVALID, "steps must be >= 1");
+    return ensure_stat_capacity(h, steps);
+}
+
 int altro_get_run_results(altro_handle_t h, int steps, int *iterations, int *iterations_outer, int *status,
                           int *ls_trials, double *cost, double *c_max, double *x0_log, double *u0_log,
                           long long *t_ns)

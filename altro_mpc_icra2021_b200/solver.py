@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "altro_get_timing", "altro_get_phase_cycles", "altro_set_trace", "altro_get_trace", "altro_snapshot", "altro_restore", "altro_set_track", "altro_mpc_transition", "altro_set_noise_bank", "altro_set_noise_model", "altro_get_x0", "altro_mpc_run",
     "altro_get_run_results",
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
-    "altro_set_line_search_mode", "altro_get_line_search_mode",
+    "altro_set_line_search_mode", "altro_get_line_search_mode", "altro_reserve_steps",
     "altro_measure_peaks",
 ]
 
@@ -378,6 +378,11 @@ class ALTROSolver:
         out = np.zeros((self.prob.B, 8), np.int64)
         self._ck(self.lib.altro_get_phase_cycles(self.h, int(enable), _p(out)))
         return out
+
+    def reserve_steps(self, steps: int):
+        """Pre-sizes the per-step statistics / log buffers (otherwise the first longer mpc_run reallocates them)."""
+        self.upload()
+        self._ck(self.lib.altro_reserve_steps(self.h, int(steps)))
 
     def launch_info(self) -> dict:
         self.upload()

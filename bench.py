@@ -366,6 +366,7 @@ def main():
         for _ in range(W):
             q_tick(True)
     if fused:
+        sv.reserve_steps(K)  # log buffers sized before the timed region (no cudaFree/cudaMalloc inside it)
         sv.snapshot()  # the lock-step and e2e phases replay the same K steps from this state
     barrier()
     # ---- timed region: K steps, CUDA events on the launching stream around every launch

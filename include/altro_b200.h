@@ -182,6 +182,9 @@ int altro_set_noise_bank(altro_handle_t h, const double *noise, int steps);
  * run).  Per-step results: statistics [steps][B], closed-loop states x0_log[steps][B][n] (X_traj of the
  * reference) and applied controls u0_log[steps][B][m], per-step device time per instance t_ns[steps][B]. */
 int altro_mpc_run(altro_handle_t h, int steps, int shift);
+/* Sizes the per-step statistics and closed-loop log buffers for runs of up to `steps` steps ahead of time, so that
+ * altro_mpc_run does not have to synchronise and reallocate when a longer run follows a shorter one. */
+int altro_reserve_steps(altro_handle_t h, int steps);
 int altro_get_run_results(altro_handle_t h, int steps, int *iterations, int *iterations_outer, int *status,
                           int *ls_trials, double *cost, double *c_max, double *x0_log, double *u0_log,
                           long long *t_ns);
