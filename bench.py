@@ -477,8 +477,11 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     ps = np.array(per_step)
     traffic = None
-    if wl.name == "rocket" and B == 4096 and fused:  # 18.75 MB per 20-step launch (ncu), state in+out once per launch
-        traffic = 18.75e6 * (0.5 + 0.5 * S_launch / 20.0)
+    if wl.name == "rocket" and B == 4096 and fused:
+        # 23.66 MB for the 20-step launch (ncu, profiles/r1_solve_kernel_ncu_metrics.json): per launch the state of the
+        # run, track and constraint data in and the solution out (18.7 MB), per step 4096 x 48 B of disturbances in
+        # and the step's closed-loop log and statistics out (0.25 MB); scaled to this launch's step count
+        traffic = 18.7e6 + 0.25e6 * S_launch
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * total_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
