@@ -142,6 +142,34 @@ function mpc_run!(s::ALTROSolver, steps::Integer; shift=true)
     fetch!(s)
 end
 
+"Quadruped: per-instance bank of linearisations + gait schedule (altro_solver.jl:40-62 without the per-tick upload)."
+function set_dynamics_slots!(s::ALTROSolver, A, Bm, d, sched::Array{Cint})
+    nslots, sched_len = size(A, 3), size(sched, 1)   # A is (n, n, nslots, B), sched is (sched_len, B) in Julia order
+    check(s.h, ccall((:altro_set_dynamics_slots, lib), Cint,
+                     (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Cint),
+                     s.h, nslots, A, Bm, d, sched, sched_len))
+end
+
+"Grasp: constraint data along the whole object trajectory, read at each instance's position (grasp_mpc_helpers.jl:46-55)."
+function add_track_constraint!(s::ALTROSolver, sense, side, knots::UnitRange, inds::Vector{<:Integer}, G, h)
+    id = Ref{Cint}(0)
+    p, w, Nt = size(G, 2), size(G, 1), size(G, 3)    # G is (w, p, Nt) in Julia order
+    check(s.h, ccall((:altro_add_track_constraint, lib), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ref{Cint}),
+                     s.h, sense, side, first(knots) - 1, last(knots), p, w, Cint.(inds .- 1), G, h, Nt, id))
+    return id[]
+end
+set_track_index!(s::ALTROSolver, kidx::Vector{Cint}) =
+    check(s.h, ccall((:altro_set_track_index, lib), Cint, (Ptr{Cvoid}, Ptr{Cint}), s.h, kidx))
+
+"Launch tuning; neither call changes a bit of the results."
+set_launch_config!(s::ALTROSolver, threads::Integer) =
+    check(s.h, ccall((:altro_set_launch_config, lib), Cint, (Ptr{Cvoid}, Cint), s.h, threads))
+set_line_search_mode!(s::ALTROSolver, speculative::Integer) =
+    check(s.h, ccall((:altro_set_line_search_mode, lib), Cint, (Ptr{Cvoid}, Cint), s.h, speculative))
+reserve_steps!(s::ALTROSolver, steps::Integer) =
+    check(s.h, ccall((:altro_reserve_steps, lib), Cint, (Ptr{Cvoid}, Cint), s.h, steps))
+
 "benchmark_solve!(solver; samples, evals): restore-and-resolve; returns device times in ms."
 function benchmark_solve!(s::ALTROSolver; samples=10, evals=10)
     push_options!(s)
