@@ -67,6 +67,7 @@ struct altro_handle_s {
     ConDesc *con_dev = nullptr;
     int *itab_dev = nullptr;
     double *ex_glob = nullptr;
+    double *ws = nullptr;  // large state dimension: [B][lay.ws_doubles]
     int P = 0, EX = 0, ITAB = 0, NSRC = 0, NTL = 0;
     bool finalized = false, have_dyn = false, have_cost = false, have_ref = false, have_x0 = false;
     // MPC track
@@ -382,6 +383,19 @@ int finalize(altro_handle_t h)
             h->lay = make_layout(n, m, N, P, ncons, 0, 0, h->ITAB);
         }
     }
+    if ((size_t)h->lay.bytes > limit) {
+        // Large state dimension: n-sized matrices and gains in a per-instance global workspace (make_layout_big).
+        if (h->ex_glob == nullptr && EX > 0) CK(h, dalloc(&h->ex_glob, (size_t)B * EX));
+        Layout lb = make_layout_big(n, m, N, P, ncons, 0);
+        if ((size_t)lb.bytes <= limit) {
+            h->lay = lb;
+            h->kernel = kernel_0_0(T);
+            h->ref_in_smem = 0;
+            h->dyn_in_smem = 0;
+            h->spec = 0;
+            CK(h, dalloc(&h->ws, (size_t)B * lb.ws_doubles));
+        }
+    }
     size_t smem = (size_t)h->lay.bytes;
     if (smem > limit) {
         char buf[256];
@@ -509,7 +523,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->x0_snap, h->xref_snap, h->uref_snap, h->kidx_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->ws, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -860,6 +874,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     }
     P.kidx = h->kidx;
     P.ex_glob = h->ex_glob;
+    P.ws = h->ws;
     P.phase = h->phase;
     P.phase_detail = getenv("ALTRO_B200_PHASE_DETAIL") ? 1 : 0;
     void *args[] = {&P};

@@ -48,6 +48,7 @@ struct Layout {
     int Qd, Qfd, Rd, sA, sB, sd, X, U, Xb, Ub, xr, ur, K, dv, lam, mu, ex, S, SA, Qxx, SB, Qux, T1, Quu, L, s, Qx, Qu,
         t1, linv, red, bc, itm, cand, Qi, cd;  // cd: offset (in doubles) of the ConDesc array, followed by the gather tables
     int bytes;                       // total dynamic shared memory
+    int big, ws_doubles;             // large state dimension: the n-sized matrices live in a global workspace (offsets into it)
 };
 
 #ifndef ALTRO_T128_CTAS
@@ -74,6 +75,36 @@ __host__ __device__ constexpr Layout fixed_layout(int n, int m)
     return l;
 }
 
+// Large state dimensions (n >= ~60: S alone no longer fits next to the trajectories): the matrices with an n-sized
+// side -- S, SA, Qxx, SB, Qux, T1, the gains K and the gathered expansion Qi -- move to a per-instance workspace in
+// global memory (L2-resident), the dynamics are read in place, the gather tables stay in global memory; vectors,
+// trajectories, duals, the m x m blocks and the descriptors stay in shared memory.  Same code, other pointers.
+__host__ __device__ inline Layout make_layout_big(int n, int m, int N, int P, int ncon, int EX)
+{
+    Layout l{};
+    int q = 0, w = 0;
+    auto take = [&](int count) { int at = q; q += count; return at; };
+    auto wtake = [&](int count) { int at = w; w += count; return at; };
+    l.Qd = take(n); l.Qfd = take(n); l.Rd = take(m); l.sd = take(n);
+    l.Quu = take(m * m); l.L = take(m * m);
+    l.s = take(n); l.Qx = take(n); l.Qu = take(m); l.t1 = take(m); l.linv = take(m);
+    l.mu = take(MAX_CON); l.bc = take(24); l.red = take(9);
+    l.X = take(N * n); l.U = take((N - 1) * m); l.Xb = take(N * n); l.Ub = take((N - 1) * m);
+    l.xr = l.ur = -1;
+    l.dv = take((N - 1) * m); l.lam = take(P); l.ex = take(EX); l.itm = take(N * (1 + ncon));
+    l.cand = q;
+    q += q & 1;
+    l.cd = q;
+    l.sA = l.sB = 0;  // unused: A_k, B_k are read where they are
+    l.S = wtake(n * n); l.SA = wtake(n * n); l.Qxx = wtake(n * n); l.SB = wtake(n * m); l.Qux = wtake(m * n);
+    l.T1 = wtake(m * n); l.Qi = wtake(n + n * n + m + m * m); l.K = wtake((N - 1) * m * n);
+    size_t b = (size_t)q * sizeof(double) + (size_t)(ncon > 0 ? ncon : 1) * sizeof(ConDesc);
+    l.bytes = (int)((b + 15) & ~(size_t)15);
+    l.big = 1;
+    l.ws_doubles = w;
+    return l;
+}
+
 __host__ __device__ inline Layout make_layout(int n, int m, int N, int P, int ncon, int EX, int ref_in_smem, int ITAB,
                                               int spec_sets = 0)
 {
@@ -93,6 +124,8 @@ __host__ __device__ inline Layout make_layout(int n, int m, int N, int P, int nc
     l.cd = q;
     size_t b = (size_t)q * sizeof(double) + (size_t)(ncon > 0 ? ncon : 1) * sizeof(ConDesc) + (size_t)ITAB * sizeof(int);
     l.bytes = (int)((b + 15) & ~(size_t)15);
+    l.big = 0;
+    l.ws_doubles = 0;
     return l;
 }
 
@@ -125,7 +158,8 @@ struct Params {
     int phase_detail;               // 1: phase[] holds the backward-pass sub-phase split instead
     long long *phase;               // optional [B][8] cycle counters per phase (profiling aid), or nullptr
     const ConDesc *con;
-    const int *itab;  // gather lists built by the host: gptr[NT+1] then gsrc[]
+    const int *itab;  // gather tables built by the host: source records, gptr[NT+1], per-knot refresh list
+    double *ws;       // large state dimension: per-instance workspace [B][lay.ws_doubles]
     Layout lay;
     int spec;  // line-search trials evaluated concurrently, one per warp (0 = sequential)
     altro_opts_t o;
@@ -290,13 +324,15 @@ struct Ctx {
             Quu = sm + f.Quu; L = sm + f.L; s = sm + f.s; Qx = sm + f.Qx; Qu = sm + f.Qu; t1 = sm + f.t1;
             linv = sm + f.linv; mu = sm + f.mu; bc = sm + f.bc; red = sm + f.red; Qi = sm + f.Qi; X = sm + f.X;
         } else {
-            Qd = sm + l.Qd; Qfd = sm + l.Qfd; Rd = sm + l.Rd; sA = sm + l.sA; sB = sm + l.sB; sd = sm + l.sd;
-            S = sm + l.S; SA = sm + l.SA; Qxx = sm + l.Qxx; SB = sm + l.SB; Qux = sm + l.Qux; T1 = sm + l.T1;
+            // run-time sized kernel: large problems keep their n-sized matrices in a global workspace
+            double *big = l.big ? P.ws + (size_t)inst * l.ws_doubles : sm;
+            Qd = sm + l.Qd; Qfd = sm + l.Qfd; Rd = sm + l.Rd; sA = big + l.sA; sB = big + l.sB; sd = sm + l.sd;
+            S = big + l.S; SA = big + l.SA; Qxx = big + l.Qxx; SB = big + l.SB; Qux = big + l.Qux; T1 = big + l.T1;
             Quu = sm + l.Quu; L = sm + l.L; s = sm + l.s; Qx = sm + l.Qx; Qu = sm + l.Qu; t1 = sm + l.t1;
-            linv = sm + l.linv; mu = sm + l.mu; bc = sm + l.bc; red = sm + l.red; Qi = sm + l.Qi; X = sm + l.X;
+            linv = sm + l.linv; mu = sm + l.mu; bc = sm + l.bc; red = sm + l.red; Qi = big + l.Qi; X = sm + l.X;
         }
         U = sm + l.U; Xb = sm + l.Xb; Ub = sm + l.Ub;
-        K = sm + l.K; dv = sm + l.dv; lam = sm + l.lam;
+        K = ((NX == 0 && l.big) ? P.ws + (size_t)inst * l.ws_doubles : sm) + l.K; dv = sm + l.dv; lam = sm + l.lam;
         if constexpr (ALL_SMEM) {
             // fixed-dimension kernels keep the reference window and the expansion blocks in shared memory, always
             // (the host routes problems that do not fit to the run-time sized kernel): every access is an LDS/STS
@@ -312,7 +348,8 @@ struct Ctx {
         ldiag = nullptr; itm = sm + l.itm; specr = bc + 8;
         cd = reinterpret_cast<ConDesc *>(sm + l.cd);
         NT = n + n * n + m + m * m;
-        grec = reinterpret_cast<int4 *>(cd + (ncon > 0 ? ncon : 1));
+        grec = (NX == 0 && l.big) ? reinterpret_cast<int4 *>(const_cast<int *>(P.itab))  // too long for shared memory
+                                  : reinterpret_cast<int4 *>(cd + (ncon > 0 ? ncon : 1));
         gptr = reinterpret_cast<int *>(grec + P.NSRC);
         gtl = gptr + NT + 1;
         dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_sched ? (size_t)P.dyn_slots : (P.dyn_per_knot ? (size_t)(N - 1) : 1)) : 0;
@@ -394,8 +431,9 @@ struct Ctx {
         int *dst = reinterpret_cast<int *>(cd);
 #pragma unroll 1
         for (int i = tid; i < words; i += T) dst[i] = src[i];
+        if (!(NX == 0 && P.lay.big))
 #pragma unroll 1
-        for (int i = tid; i < P.ITAB; i += T) reinterpret_cast<int *>(grec)[i] = P.itab[i];
+            for (int i = tid; i < P.ITAB; i += T) reinterpret_cast<int *>(grec)[i] = P.itab[i];
 #pragma unroll 1
         for (int t = tid; t < NT; t += T) {  // matrix entries no block touches keep the cost Hessian for the whole launch
             double base = 0.0;
@@ -763,7 +801,7 @@ struct Ctx {
     // the warps that would idle while warp 0 factorises Quu of knot k+1 prepare knot k (backward_pass, P3).
     __device__ __forceinline__ void prep_knot(int k, int t0, int stride)
     {
-        if (!P.dyn_in_smem) {  // d_k is not needed by the backward pass
+        if (!P.dyn_in_smem && !(NX == 0 && P.lay.big)) {  // d_k is not needed by the backward pass
             const double *gA = as_global(P.A) + dyn_index(k) * n * n;
             const double *gB = as_global(P.Bm) + dyn_index(k) * n * m;
 #pragma unroll 2
@@ -834,7 +872,7 @@ struct Ctx {
         const int fr = lane >> 2, fc = 2 * (lane & 3);  // this lane's row / first column inside a tile
         const int tn = (n + 7) >> 3, tm = (m + 7) >> 3, tn1 = (n + 8) >> 3, tm1 = (m + 8) >> 3;
         const int oQxx = n, oQu = n + n * n, oQuu = n + n * n + m;
-        const double *A = sA, *Bm = sB;  // always shared memory here (LTV knots are staged below)
+        const double *A = sA, *Bm = sB;  // shared memory (LTV knots are staged by prep_knot), except for large problems
         for (;;) {
             bool restart = false;
             double a1 = 0.0, a2 = 0.0;  // dV accumulators, kept by thread T-1
@@ -859,6 +897,10 @@ struct Ctx {
 #else
 #define ALTRO_TICK(slot) do { (void)tq; (void)tq2; } while (0)
 #endif
+                if (NX == 0 && P.lay.big) {  // large state dimension: the dynamics are read where they are
+                    A = P.A + dyn_index(k) * n * n;
+                    Bm = P.Bm + dyn_index(k) * n * m;
+                }
                 // P1: SA = S A, SB = S B (tensor tiles); A_k, B_k and Qi were prepared during the previous knot
                 for (int t = warp; t < tn * (tn + tm); t += NW) {
                     const int r0 = (t / (tn + tm)) << 3, ct = t % (tn + tm);

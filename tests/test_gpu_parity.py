@@ -129,6 +129,15 @@ def test_odd_dimensions_use_the_runtime_kernel(n, m, N):
     solve_both(lqr_problem(n=n, m=m, N=N, batch=7, seed=n + m, u_bnd=0.4), SolverOptions(constraint_tolerance=1e-6))
 
 
+@pytest.mark.parametrize("n,m,N", [(64, 8, 11), (100, 20, 9), (200, 25, 6)])
+def test_large_state_dimensions_use_the_global_workspace(n, m, N):
+    """n >= 64: S no longer fits in shared memory; the n-sized matrices and the gains live in a per-instance global
+    workspace (make_layout_big) and the Riccati products are real FP64 tensor-core GEMM tiles.  Same bits."""
+    prob = lqr_problem(n=n, m=m, N=N, batch=3, seed=n + m, u_bnd=0.4)
+    _, g, _ = solve_both(prob, SolverOptions(constraint_tolerance=1e-6))
+    assert g.launch_info()["smem_bytes"] < 227 * 1024
+
+
 # ------------------------------------------------------------------ edge cases
 
 def test_single_instance_and_unconstrained():
