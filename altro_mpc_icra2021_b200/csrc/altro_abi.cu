@@ -103,6 +103,21 @@ cudaError_t dalloc(Tp **p, size_t count)
 {
     cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(Tp));
     if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(Tp));
+    // The memset runs on the null stream and is asynchronous to the host; the handle's kernels run on their own
+    // (possibly non-blocking) stream.  Without this wait a late memset can zero what a kernel already wrote
+    // (observed: an all-zero u0 log once in ~100 runs).
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return e;
+}
+
+// Set-up copies (descriptors, tables, constraint data, tracks).  cudaMemcpy runs on the null stream, with which the
+// handle's non-blocking stream does not synchronise, and may return before the DMA of a pageable buffer has landed:
+// wait for the device on both sides so that no launch on the handle's stream can overtake or be overtaken.
+inline cudaError_t copy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, kind);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     return e;
 }
 
@@ -326,10 +341,10 @@ int finalize(altro_handle_t h)
         itab.insert(itab.end(), tl.begin(), tl.end());
         h->ITAB = (int)itab.size();
         CK(h, dalloc(&h->itab_dev, itab.size()));
-        CK(h, cudaMemcpy(h->itab_dev, itab.data(), itab.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(h, copy_sync(h->itab_dev, itab.data(), itab.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     CK(h, dalloc(&h->con_dev, cd.size()));
-    CK(h, cudaMemcpy(h->con_dev, cd.data(), cd.size() * sizeof(ConDesc), cudaMemcpyHostToDevice));
+    CK(h, copy_sync(h->con_dev, cd.data(), cd.size() * sizeof(ConDesc), cudaMemcpyHostToDevice));
     CK(h, dalloc(&h->lam, (size_t)B * P));
     CK(h, dalloc(&h->lam_snap, (size_t)B * P));
     // launch geometry
@@ -689,13 +704,13 @@ int altro_add_constraint(altro_handle_t h, int sense, int side, int k0, int k1, 
         return fail(h, ALTRO_ERR_UNSUPPORTED, "dense constraint block larger than 8 rows x 8 indices");
     CK(h, dalloc(&c.G_dev, c.g_count));
     CK(h, dalloc(&c.h_dev, c.h_count));
-    CK(h, cudaMemcpy(c.G_dev, G, c.g_count * sizeof(double), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(c.h_dev, hv, c.h_count * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, copy_sync(c.G_dev, G, c.g_count * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, copy_sync(c.h_dev, hv, c.h_count * sizeof(double), cudaMemcpyHostToDevice));
     if (c.rowsparse) {
         CK(h, dalloc(&c.rs_col_dev, p));
         CK(h, dalloc(&c.rs_coef_dev, p));
-        CK(h, cudaMemcpy(c.rs_col_dev, c.rs_col.data(), p * sizeof(int), cudaMemcpyHostToDevice));
-        CK(h, cudaMemcpy(c.rs_coef_dev, c.rs_coef.data(), p * sizeof(double), cudaMemcpyHostToDevice));
+        CK(h, copy_sync(c.rs_col_dev, c.rs_col.data(), p * sizeof(int), cudaMemcpyHostToDevice));
+        CK(h, copy_sync(c.rs_coef_dev, c.rs_coef.data(), p * sizeof(double), cudaMemcpyHostToDevice));
     }
     h->cons.push_back(c);
     if (con_id) *con_id = (int)h->cons.size() - 1;
@@ -1013,9 +1028,9 @@ int altro_get_phase_cycles(altro_handle_t h, int enable, long long *out)
 {
     REQ(h);
     CK(h, cudaStreamSynchronize(h->stream));
-    if (out && h->phase) CK(h, cudaMemcpy(out, h->phase, (size_t)h->B * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (out && h->phase) CK(h, copy_sync(out, h->phase, (size_t)h->B * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     if (enable && !h->phase) CK(h, dalloc(&h->phase, (size_t)h->B * 8));
-    if (enable) CK(h, cudaMemset(h->phase, 0, (size_t)h->B * 8 * sizeof(long long)));
+    if (enable) CK(h, cudaMemsetAsync(h->phase, 0, (size_t)h->B * 8 * sizeof(long long), h->stream));
     if (!enable && h->phase) { cudaFree(h->phase); h->phase = nullptr; }
     return ALTRO_OK;
 }
@@ -1065,9 +1080,9 @@ int altro_set_track(altro_handle_t h, const double *tX, const double *tU, int Nt
         memcpy(&pu[(size_t)k * h->m], tU + (size_t)std::min(k, Nt - 2) * h->m, h->m * sizeof(double));
     CK(h, dalloc(&h->trackX, px.size()));
     CK(h, dalloc(&h->trackU, pu.size()));
-    CK(h, cudaMemcpy(h->trackX, px.data(), px.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->trackU, pu.data(), pu.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->kidx, k_start, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice));
+    CK(h, copy_sync(h->trackX, px.data(), px.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, copy_sync(h->trackU, pu.data(), pu.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, copy_sync(h->kidx, k_start, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice));
     h->Nt = Nt;
     return ALTRO_OK;
 }

@@ -8,12 +8,15 @@ from altro_mpc_icra2021_b200.problems import mpc, random_linear
 from oracle.oracle import OracleProblem
 
 points = [(2, 2), (15, 2), (25, 2), (35, 2), (45, 2), (55, 2), (30, 2), (30, 6), (30, 10), (30, 15), (30, 20), (30, 25),
-          (64, 16), (100, 25)]
-B = int(os.environ.get("B", "1024")); K = int(os.environ.get("K", "10"))
+          (64, 16), (100, 25), (128, 32), (200, 25)]
+if os.environ.get("POINTS"):
+    points = [tuple(int(v) for v in p.split("x")) for p in os.environ["POINTS"].split(",")]
+B0 = int(os.environ.get("B", "1024")); K0 = int(os.environ.get("K", "10"))
 nthreads = len(os.sched_getaffinity(0))
 print("| n | m | N | batch | threads/inst | smem/inst KB | GPU solves/s | p50 us | CPU solves/s (%d cores) | speed-up | iters | bit-identical |" % nthreads)
 print("|---|---|---|---|---|---|---|---|---|---|---|---|")
 for n, m in points:
+    B, K = (B0, K0) if n < 64 else (min(B0, 296), min(K0, 4))  # large points: the CPU side is O(n^3) per knot
     try:
         prob, Xt, Ut, ks = random_linear.mpc_problem(n, m, 21, batch=B, seed=500 + n + m)
         opts = random_linear.mpc_options()

@@ -287,8 +287,14 @@ def test_abi_rejects_bad_arguments():
     assert lib.altro_destroy(h) == 0
 
 
+def test_long_horizon_with_wide_gains_uses_the_global_workspace():
+    """n = 40, m = 30, N = 101: the gains alone (100 x 30 x 40 doubles) exceed shared memory -> workspace layout."""
+    solve_both(lqr_problem(n=40, m=30, N=101, batch=2, seed=1, u_bnd=0.4), SolverOptions(constraint_tolerance=1e-6))
+
+
 def test_oversized_problem_is_an_error_not_a_fallback():
-    prob = lqr_problem(n=40, m=30, N=101, batch=2, seed=1)
+    # the trajectories themselves (2 x N x (n + m) doubles) must fit in shared memory even with the global workspace
+    prob = lqr_problem(n=200, m=20, N=121, batch=2, seed=1)
     from altro_mpc_icra2021_b200.solver import AltroError
 
     with pytest.raises(AltroError, match="shared memory"):
