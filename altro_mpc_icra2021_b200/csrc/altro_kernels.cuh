@@ -859,6 +859,52 @@ struct Ctx {
         }
     }
 
+    // Register-blocked tile GEMM for the large-dimension path:  C(i,j) = init(i,j) + sum_l a1(i,l) b1(l,j)
+    // [+ sum_l a2(i,l) b2(l,j)], every chain over ascending l exactly like mma_chain.  A warp owns a 16 x 16 block of C
+    // (2 x 2 DMMA tiles: two A and two B fragments feed four independent accumulator chains per k-step), the
+    // blocks are dealt round-robin to the warps.  Operand functors return 0.0 outside the matrix.
+    template <class FI, class FA1, class FB1, class FA2, class FB2, class FS>
+    __device__ __forceinline__ void tile_gemm(int M, int Nc, FI init, int K1, FA1 a1, FB1 b1, int K2, FA2 a2, FB2 b2,
+                                              FS store) const
+    {
+        const int lane = tid & 31, r = lane >> 2, q = lane & 3, fc = 2 * q;
+        const int nt = (Nc + 15) >> 4, nblk = ((M + 15) >> 4) * nt;
+#pragma unroll 1
+        for (int t = tid >> 5; t < nblk; t += T / 32) {
+            const int i0 = (t / nt) << 4, j0 = (t - (t / nt) * nt) << 4;
+            double c[2][2][2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    c[a][b][0] = init(i0 + 8 * a + r, j0 + 8 * b + fc);
+                    c[a][b][1] = init(i0 + 8 * a + r, j0 + 8 * b + fc + 1);
+                }
+            auto step = [&](double x0, double x1, double y0, double y1) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c[a][b][0]), "+d"(c[a][b][1])
+                                     : "d"(a ? x1 : x0), "d"(b ? y1 : y0));
+            };
+#pragma unroll 2
+            for (int k0 = 0; k0 < K1; k0 += 4)
+                step(a1(i0 + r, k0 + q), a1(i0 + 8 + r, k0 + q), b1(k0 + q, j0 + r), b1(k0 + q, j0 + 8 + r));
+#pragma unroll 2
+            for (int k0 = 0; k0 < K2; k0 += 4)
+                step(a2(i0 + r, k0 + q), a2(i0 + 8 + r, k0 + q), b2(k0 + q, j0 + r), b2(k0 + q, j0 + 8 + r));
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    store(i0 + 8 * a + r, j0 + 8 * b + fc, c[a][b][0]);
+                    store(i0 + 8 * a + r, j0 + 8 * b + fc + 1, c[a][b][1]);
+                }
+        }
+    }
+
     // Returns false if Quu could not be made positive definite.
     __device__ bool backward_pass(double &rho, double &drho, double &dV1, double &dV2)
     {
@@ -901,8 +947,21 @@ struct Ctx {
                     A = P.A + dyn_index(k) * n * n;
                     Bm = P.Bm + dyn_index(k) * n * m;
                 }
+                constexpr bool MAYBE_BIG = NX == 0;
+                const bool big = MAYBE_BIG && P.lay.big;
+                auto zero_a = [](int, int) { return 0.0; };
                 // P1: SA = S A, SB = S B (tensor tiles); A_k, B_k and Qi were prepared during the previous knot
-                for (int t = warp; t < tn * (tn + tm); t += NW) {
+                if (big) {
+                    tile_gemm(n, n, [](int, int) { return 0.0; }, n,
+                              [&](int i, int l) { return (i < n && l < n) ? S[i * n + l] : 0.0; },
+                              [&](int l, int j) { return (l < n && j < n) ? A[l * n + j] : 0.0; }, 0, zero_a, zero_a,
+                              [&](int i, int j, double v) { if (i < n && j < n) SA[i * n + j] = v; });
+                    tile_gemm(n, m, [](int, int) { return 0.0; }, n,
+                              [&](int i, int l) { return (i < n && l < n) ? S[i * n + l] : 0.0; },
+                              [&](int l, int j) { return (l < n && j < m) ? Bm[l * m + j] : 0.0; }, 0, zero_a, zero_a,
+                              [&](int i, int j, double v) { if (i < n && j < m) SB[i * m + j] = v; });
+                }
+                for (int t = warp; !big && t < tn * (tn + tm); t += NW) {
                     const int r0 = (t / (tn + tm)) << 3, ct = t % (tn + tm);
                     const int i = r0 + fr;
                     double d0 = 0.0, d1 = 0.0;
@@ -931,7 +990,30 @@ struct Ctx {
                 // P2: [Qxx | Qx] += A'[SA | s],  Qux = B'SA,  [Quu | Qu] += B'[SB | s]   (chains start from the
                 //     cost + AL expansion already in Qxx / Qx / Quu / Qu)
                 const int nt_xx = tn * tn1, nt_ux = tm * tn, nt_uu = tm * tm1;
-                for (int t = warp; t < nt_xx + nt_ux + nt_uu; t += NW) {
+                if (big) {
+                    tile_gemm(n, n + 1,
+                              [&](int i, int j) { return i < n ? (j < n ? Qi[oQxx + i * n + j] : (j == n ? Qi[i] : 0.0)) : 0.0; }, n,
+                              [&](int i, int l) { return (i < n && l < n) ? A[l * n + i] : 0.0; },
+                              [&](int l, int j) { return (l < n && j <= n) ? (j < n ? SA[l * n + j] : s[l]) : 0.0; },
+                              0, zero_a, zero_a,
+                              [&](int i, int j, double v) { if (i < n) { if (j < n) Qxx[i * n + j] = v; else if (j == n) Qx[i] = v; } });
+                    tile_gemm(m, n, [](int, int) { return 0.0; }, n,
+                              [&](int i, int l) { return (i < m && l < n) ? Bm[l * m + i] : 0.0; },
+                              [&](int l, int j) { return (l < n && j < n) ? SA[l * n + j] : 0.0; }, 0, zero_a, zero_a,
+                              [&](int i, int j, double v) { if (i < m && j < n) Qux[i * n + j] = v; });
+                    tile_gemm(m, m + 1,
+                              [&](int i, int j) { return i < m ? (j < m ? Qi[oQuu + i * m + j] : (j == m ? Qi[oQu + i] : 0.0)) : 0.0; }, n,
+                              [&](int i, int l) { return (i < m && l < n) ? Bm[l * m + i] : 0.0; },
+                              [&](int l, int j) { return (l < n && j <= m) ? (j < m ? SB[l * m + j] : s[l]) : 0.0; },
+                              0, zero_a, zero_a,
+                              [&](int i, int j, double v) {
+                                  if (i < m) {
+                                      if (j < m) { Quu[i * m + j] = v; L[i * m + j] = v + ((i == j) ? rho : 0.0); }
+                                      else if (j == m) Qu[i] = v;
+                                  }
+                              });
+                }
+                for (int t = warp; !big && t < nt_xx + nt_ux + nt_uu; t += NW) {
                     if (t < nt_xx) {
                         const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
                         const int i = r0 + fr, j = c0 + fc;
@@ -1108,7 +1190,14 @@ struct Ctx {
                 gsync<T>();
                 ALTRO_TICK(4);
                 // P5: [T1 | t1] = Quu [K | d] + [Qux | Qu]
-                for (int t = warp; t < tm * tn1; t += NW) {
+                if (big)
+                    tile_gemm(m, n + 1,
+                              [&](int i, int j) { return i < m ? (j < n ? Qux[i * n + j] : (j == n ? Qu[i] : 0.0)) : 0.0; }, m,
+                              [&](int i, int l) { return (i < m && l < m) ? Quu[i * m + l] : 0.0; },
+                              [&](int l, int j) { return (l < m && j <= n) ? (j < n ? Kk[l * n + j] : dk_[l]) : 0.0; },
+                              0, zero_a, zero_a,
+                              [&](int i, int j, double v) { if (i < m) { if (j < n) T1[i * n + j] = v; else if (j == n) t1[i] = v; } });
+                for (int t = warp; !big && t < tm * tn1; t += NW) {
                     const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
                     const int i = r0 + fr, j = c0 + fc;
                     double d0 = (i < m) ? (j < n ? Qux[i * n + j] : (j == n ? Qu[i] : 0.0)) : 0.0;
@@ -1130,7 +1219,27 @@ struct Ctx {
                 ALTRO_TICK(5);
                 // P6: [S' | s] = [Qxx | Qx] + K'[T1 | t1] + Qux'[K | d]; the transposed tile is chained in the same
                 //     lanes so that S = (S' + S'^T)/2 needs no second pass.  dV += [d'Qu, 1/2 d'Quu d].
-                for (int t = warp; t < tn * tn1; t += NW) {
+                if (big) {
+                    // D = [Qxx | Qx] + K'[T1 | t1] + Qux'[K | d] into SA (free since P2) and s; E = Qxx' + T1'K + K'Qux
+                    // into S (not read since P1); then S = (D + E)/2 element by element.
+                    tile_gemm(n, n + 1,
+                              [&](int i, int j) { return i < n ? (j < n ? Qxx[i * n + j] : (j == n ? Qx[i] : 0.0)) : 0.0; }, m,
+                              [&](int i, int l) { return (i < n && l < m) ? Kk[l * n + i] : 0.0; },
+                              [&](int l, int j) { return (l < m && j <= n) ? (j < n ? T1[l * n + j] : t1[l]) : 0.0; }, m,
+                              [&](int i, int l) { return (i < n && l < m) ? Qux[l * n + i] : 0.0; },
+                              [&](int l, int j) { return (l < m && j <= n) ? (j < n ? Kk[l * n + j] : dk_[l]) : 0.0; },
+                              [&](int i, int j, double v) { if (i < n) { if (j < n) SA[i * n + j] = v; else if (j == n) s[i] = v; } });
+                    tile_gemm(n, n, [&](int i, int j) { return (i < n && j < n) ? Qxx[j * n + i] : 0.0; }, m,
+                              [&](int i, int l) { return (i < n && l < m) ? T1[l * n + i] : 0.0; },
+                              [&](int l, int j) { return (l < m && j < n) ? Kk[l * n + j] : 0.0; }, m,
+                              [&](int i, int l) { return (i < n && l < m) ? Kk[l * n + i] : 0.0; },
+                              [&](int l, int j) { return (l < m && j < n) ? Qux[l * n + j] : 0.0; },
+                              [&](int i, int j, double v) { if (i < n && j < n) S[i * n + j] = v; });
+                    gsync<T>();
+#pragma unroll 2
+                    for (int e = tid; e < n * n; e += T) S[e] = 0.5 * (SA[e] + S[e]);
+                }
+                for (int t = warp; !big && t < tn * tn1; t += NW) {
                     const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
                     const int i = r0 + fr, j = c0 + fc;
                     double d0 = (i < n) ? (j < n ? Qxx[i * n + j] : (j == n ? Qx[i] : 0.0)) : 0.0;
