@@ -54,6 +54,9 @@ struct Layout {
 #ifndef ALTRO_T128_CTAS
 #define ALTRO_T128_CTAS 4  // resident CTAs per SM the 128-thread small-dimension kernels are register-capped for
 #endif
+#ifndef ALTRO_GEN256_CTAS
+#define ALTRO_GEN256_CTAS 2  // resident CTAs per SM the 256-thread run-time sized kernel is register-capped for
+#endif
 #ifndef ALTRO_FIXED_ALL_SMEM
 #define ALTRO_FIXED_ALL_SMEM 1
 #endif
@@ -889,10 +892,10 @@ struct Ctx {
                                      : "+d"(c[a][b][0]), "+d"(c[a][b][1])
                                      : "d"(a ? x1 : x0), "d"(b ? y1 : y0));
             };
-#pragma unroll 2
+#pragma unroll 4
             for (int k0 = 0; k0 < K1; k0 += 4)
                 step(a1(i0 + r, k0 + q), a1(i0 + 8 + r, k0 + q), b1(k0 + q, j0 + r), b1(k0 + q, j0 + 8 + r));
-#pragma unroll 2
+#pragma unroll 4
             for (int k0 = 0; k0 < K2; k0 += 4)
                 step(a2(i0 + r, k0 + q), a2(i0 + 8 + r, k0 + q), b2(k0 + q, j0 + r), b2(k0 + q, j0 + 8 + r));
 #pragma unroll
@@ -1674,7 +1677,7 @@ template <int NX, int NU, int T>
 // (measured, scripts/dev_perf.py): quadruped (12,12) is fastest with the whole register file at 4 CTAs/SM; the other
 // 12-dimensional and run-time sized problems with a 168-register cap (6 CTAs/SM at T = 64).
 __global__ void __launch_bounds__(T, ((NX == 12 && NU == 12) ? (256 / T > 0 ? 256 / T : 1)
-                                      : (NX >= 12 || NX == 0) ? (384 / T > 0 ? 384 / T : 1) : (T == 128 ? ALTRO_T128_CTAS : 512 / T))) altro_solve_kernel(const __grid_constant__ Params P)
+                                      : (NX == 0 && T == 256) ? ALTRO_GEN256_CTAS : (NX >= 12 || NX == 0) ? (384 / T > 0 ? 384 / T : 1) : (T == 128 ? ALTRO_T128_CTAS : 512 / T))) altro_solve_kernel(const __grid_constant__ Params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<NX, NU, T> ctx(P, smem_raw);
