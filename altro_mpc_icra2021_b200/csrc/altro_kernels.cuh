@@ -863,45 +863,54 @@ struct Ctx {
     }
 
     // Register-blocked tile GEMM for the large-dimension path:  C(i,j) = init(i,j) + sum_l a1(i,l) b1(l,j)
-    // [+ sum_l a2(i,l) b2(l,j)], every chain over ascending l exactly like mma_chain.  A warp owns a 16 x 16 block of C
-    // (2 x 2 DMMA tiles: two A and two B fragments feed four independent accumulator chains per k-step), the
+    // [+ sum_l a2(i,l) b2(l,j)], every chain over ascending l exactly like mma_chain.  A warp owns a 16 x 32 block of C
+    // (2 x 4 DMMA tiles: two A and four B fragments feed eight independent accumulator chains per k-step), the
     // blocks are dealt round-robin to the warps.  Operand functors return 0.0 outside the matrix.
     template <class FI, class FA1, class FB1, class FA2, class FB2, class FS>
     __device__ __forceinline__ void tile_gemm(int M, int Nc, FI init, int K1, FA1 a1, FB1 b1, int K2, FA2 a2, FB2 b2,
                                               FS store) const
     {
+        constexpr int NB = 4;  // a warp owns 16 x (8 NB) of C: 2 A and NB B fragments feed 2 NB accumulator chains
         const int lane = tid & 31, r = lane >> 2, q = lane & 3, fc = 2 * q;
-        const int nt = (Nc + 15) >> 4, nblk = ((M + 15) >> 4) * nt;
+        const int nt = (Nc + 8 * NB - 1) / (8 * NB), nblk = ((M + 15) >> 4) * nt;
 #pragma unroll 1
         for (int t = tid >> 5; t < nblk; t += T / 32) {
-            const int i0 = (t / nt) << 4, j0 = (t - (t / nt) * nt) << 4;
-            double c[2][2][2];
+            const int i0 = (t / nt) << 4, j0 = (t - (t / nt) * nt) * (8 * NB);
+            double c[2][NB][2];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
+                for (int b = 0; b < NB; ++b) {
                     c[a][b][0] = init(i0 + 8 * a + r, j0 + 8 * b + fc);
                     c[a][b][1] = init(i0 + 8 * a + r, j0 + 8 * b + fc + 1);
                 }
-            auto step = [&](double x0, double x1, double y0, double y1) {
+            auto step = [&](double x0, double x1, const double (&y)[NB]) {
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
-#pragma unroll
-                    for (int b = 0; b < 2; ++b)
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                     : "+d"(c[a][b][0]), "+d"(c[a][b][1])
-                                     : "d"(a ? x1 : x0), "d"(b ? y1 : y0));
+                for (int b = 0; b < NB; ++b) {
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[0][b][0]), "+d"(c[0][b][1]) : "d"(x0), "d"(y[b]));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[1][b][0]), "+d"(c[1][b][1]) : "d"(x1), "d"(y[b]));
+                }
             };
-#pragma unroll 4
-            for (int k0 = 0; k0 < K1; k0 += 4)
-                step(a1(i0 + r, k0 + q), a1(i0 + 8 + r, k0 + q), b1(k0 + q, j0 + r), b1(k0 + q, j0 + 8 + r));
-#pragma unroll 4
-            for (int k0 = 0; k0 < K2; k0 += 4)
-                step(a2(i0 + r, k0 + q), a2(i0 + 8 + r, k0 + q), b2(k0 + q, j0 + r), b2(k0 + q, j0 + 8 + r));
+#pragma unroll 2
+            for (int k0 = 0; k0 < K1; k0 += 4) {
+                double y[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) y[b] = b1(k0 + q, j0 + 8 * b + r);
+                step(a1(i0 + r, k0 + q), a1(i0 + 8 + r, k0 + q), y);
+            }
+#pragma unroll 2
+            for (int k0 = 0; k0 < K2; k0 += 4) {
+                double y[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) y[b] = b2(k0 + q, j0 + 8 * b + r);
+                step(a2(i0 + r, k0 + q), a2(i0 + 8 + r, k0 + q), y);
+            }
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
+                for (int b = 0; b < NB; ++b) {
                     store(i0 + 8 * a + r, j0 + 8 * b + fc, c[a][b][0]);
                     store(i0 + 8 * a + r, j0 + 8 * b + fc + 1, c[a][b][1]);
                 }
