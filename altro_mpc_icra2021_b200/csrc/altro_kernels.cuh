@@ -11,6 +11,7 @@
 // Template <NX, NU, T>: state / control dimension (0 = run-time value from Params) and threads per
 // instance (32 = one warp, __syncwarp only; 64..256 = CTA with __syncthreads).
 #pragma once
+#include <type_traits>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -870,7 +871,15 @@ struct Ctx {
     __device__ __forceinline__ void tile_gemm(int M, int Nc, FI init, int K1, FA1 a1, FB1 b1, int K2, FA2 a2, FB2 b2,
                                               FS store) const
     {
-        constexpr int NB = 4;  // a warp owns 16 x (8 NB) of C: 2 A and NB B fragments feed 2 NB accumulator chains
+        // a warp owns 16 x (8 NB) of C: 2 A and NB B fragments feed 2 NB accumulator chains.  Measured: 16 x 32 blocks
+        // pay from n = 128 up, 16 x 16 below (more blocks to deal out to the warps).
+        if (n >= 128) tile_gemm_nb(std::integral_constant<int, 4>{}, M, Nc, init, K1, a1, b1, K2, a2, b2, store);
+        else tile_gemm_nb(std::integral_constant<int, 2>{}, M, Nc, init, K1, a1, b1, K2, a2, b2, store);
+    }
+    template <int NB, class FI, class FA1, class FB1, class FA2, class FB2, class FS>
+    __device__ __forceinline__ void tile_gemm_nb(std::integral_constant<int, NB>, int M, int Nc, FI init, int K1, FA1 a1,
+                                                 FB1 b1, int K2, FA2 a2, FB2 b2, FS store) const
+    {
         const int lane = tid & 31, r = lane >> 2, q = lane & 3, fc = 2 * q;
         const int nt = (Nc + 8 * NB - 1) / (8 * NB), nblk = ((M + 15) >> 4) * nt;
 #pragma unroll 1
