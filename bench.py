@@ -268,7 +268,8 @@ def main():
     ap.add_argument("--workload", default="rocket")
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     ap.add_argument("--threads-per-instance", type=int, default=0)
-    ap.add_argument("--cpu-steps", type=int, default=8, help="MPC steps of the CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=0,
+                    help="MPC steps of the CPU-baseline sample (0 = sized for about 20 core-seconds of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -522,9 +523,13 @@ def main():
         line["lockstep"] = lock
     if world == 1 and not args.no_cpu_baseline:
         nt = host_threads()
-        r = oracle_arm(Workload(args.workload, args.batch, seed, make_solver), args.cpu_steps, 1, nt)
+        cpu_steps = args.cpu_steps
+        if cpu_steps <= 0:  # probe 4 steps, then size the sample for about 20 core-seconds (bounded by K)
+            probe = oracle_arm(Workload(args.workload, args.batch, seed, make_solver), 4, 1, nt)
+            cpu_steps = int(min(max(4, round(20.0 / nt * probe["value"] / B)), max(K, 4)))
+        r = oracle_arm(Workload(args.workload, args.batch, seed, make_solver), cpu_steps, 1, nt)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": nt, "kind": "port",
-                                "sample": f"{args.cpu_steps} MPC steps x {B} instances of the same workload, CPU oracle "
+                                "sample": f"{cpu_steps} MPC steps x {B} instances of the same workload, CPU oracle "
                                           f"(oracle/altro_oracle.c, pthreads over instances), {r['seconds']:.2f} s",
                                 "iters_mean": r["iters_mean"]}
     print(json.dumps(line))
