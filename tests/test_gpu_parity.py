@@ -113,6 +113,38 @@ def test_speculative_line_search_does_not_change_bits(family, spec, threads):
     assert np.array_equal(g.stats.ls_trials, o.stats.ls_trials)
 
 
+def test_speculative_line_search_on_long_horizon_family():
+    """Flexible satellite (n = 12, m = 3, N = 40 here): 4 warps per instance, 4 trial steps at a time."""
+    prob, opts, _, _ = cases.case_flexsat(batch=6)
+    for spec in (False, True):
+        _, g, o = solve_both(copy.deepcopy(prob), opts, threads_per_instance=128, speculative_line_search=spec)
+        assert np.array_equal(g.stats.ls_trials, o.stats.ls_trials)
+
+
+def test_repeated_runs_are_identical_and_logs_survive_reallocation():
+    """The same closed-loop run from the same state twice, the second one after the log buffers were re-sized:
+    identical bits, no stale or zeroed log (guards the null-stream memset race fixed in dalloc)."""
+    cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+    runs = []
+    B = 64
+    ks = mpc.rng_for(11, 0).integers(0, cold["X"].shape[0] - 21 - 110, size=B)
+    noise = mpc.rng_for(3, 3).standard_normal((7, B, 6))
+    for reserve in (0, 12, 0):
+        prob, opts, _, _ = cases.case_rocket_mpc(cold["X"], cold["U"], batch=B)
+        sv = gpu_solver(prob, opts).solve()
+        sv.set_track(cold["X"], cold["U"], ks)
+        sv.set_noise_model(2, 1e-3, 1e-2)
+        sv.set_noise_bank(noise)
+        if reserve:
+            sv.reserve_steps(reserve)
+        sv.mpc_run(2)
+        runs.append(sv.mpc_run(5))
+        sv.close()
+    for k in ("iterations", "ls_trials", "status", "cost", "c_max", "x0", "u0"):
+        assert np.array_equal(runs[0][k], runs[1][k]) and np.array_equal(runs[0][k], runs[2][k]), k
+    assert np.abs(runs[0]["u0"]).max() > 0
+
+
 def test_runtime_dimension_kernel_matches_compiled_dimensions(monkeypatch):
     prob, opts, _, _ = cases.case_random_linear(batch=8)
     ref = copy.deepcopy(prob)
