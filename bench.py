@@ -502,7 +502,8 @@ def main():
         "gpu_launches": int(2 * n_launch if fused else 2 * K),
         "steps_per_launch": S_launch,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peaks["dfma_tflops"], "unit": "TFLOP/s",
+        # "tensor" = the compute roofline of the two the contract names; here it is the FP64 one (DFMA + DMMA m8n8k4)
+        "roofline": {"bound": "tensor", "pipe": "fp64", "achieved": achieved, "peak": peaks["dfma_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["dfma_tflops"], "traffic": traffic,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the "
                                      "20-step rocket launch (profiles/r1_summary.md), scaled to this launch's step count",
