@@ -427,7 +427,7 @@ static void expand_constraints(const orc_problem_t *pb, const orc_opts_t *o, ws_
                         H[j * wd + i] = acc;
                     }
             } else {
-                double lb[ORC_MAX_W], q[ORC_MAX_W];
+                double lb[ORC_MAX_W] = {0.0}, q[ORC_MAX_W];  /* a cone has p >= 1 rows; the initialiser only quiets -Wmaybe-uninitialized */
                 double a2 = 0.0;
                 for (int r = 0; r < p; ++r) {
                     lb[r] = l[r] - mu * row_value(c, G, h, z, r);
