@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -58,6 +60,8 @@ struct altro_handle_s {
     double *cost = nullptr, *cost_al = nullptr, *cmax = nullptr, *penmax = nullptr;
     long long *t_ns = nullptr;
     int stat_cap = 1;  // statistics arrays hold stat_cap x B entries (one slot per step of a closed-loop run)
+    int last_run_steps = 0;       // steps of the last launch if it was a closed-loop run, else 0
+    bool pending_transition = false;  // altro_mpc_transition done, its solve not yet launched
     double *x0_log = nullptr, *u0_log = nullptr;
     long long *phase = nullptr;
     double *trace = nullptr;
@@ -276,6 +280,21 @@ const void *find_kernel(int n, int m, int T)
     return kernel_0_0(T);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-kernel, process-wide state shared by every handle that uses the
+// same <NX, NU, T> instantiation: keep a running maximum and never lower it, so that a handle with a smaller horizon
+// finalised later cannot invalidate the launches of an earlier one.
+cudaError_t raise_smem_limit(const void *kernel, int bytes)
+{
+    static std::mutex mu;
+    static std::map<const void *, int> cur;
+    std::lock_guard<std::mutex> lock(mu);
+    int &c = cur[kernel];
+    if (bytes <= c) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) c = bytes;
+    return e;
+}
+
 int finalize(altro_handle_t h)
 {
     if (h->finalized) return ALTRO_OK;
@@ -345,8 +364,8 @@ int finalize(altro_handle_t h)
     }
     CK(h, dalloc(&h->con_dev, cd.size()));
     CK(h, copy_sync(h->con_dev, cd.data(), cd.size() * sizeof(ConDesc), cudaMemcpyHostToDevice));
-    CK(h, dalloc(&h->lam, (size_t)B * P));
-    CK(h, dalloc(&h->lam_snap, (size_t)B * P));
+    CK(h, dalloc(&h->lam, (size_t)B * std::max(P, 1)));  // copy_state moves B * max(P, 1) doubles
+    CK(h, dalloc(&h->lam_snap, (size_t)B * std::max(P, 1)));
     // launch geometry
     cudaDeviceProp prop;
     CK(h, cudaGetDeviceProperties(&prop, h->device));
@@ -379,7 +398,7 @@ int finalize(altro_handle_t h)
         if (const char *e = getenv("ALTRO_B200_SPEC")) want = atoi(e) ? 1 : 0;
         if (want < 0 && (size_t)ls.bytes <= limit) {
             int nb0 = 0, nb1 = 0;
-            CK(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ls.bytes));
+            CK(h, raise_smem_limit(h->kernel, ls.bytes));
             CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, h->kernel, T, (size_t)h->lay.bytes));
             CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, h->kernel, T, (size_t)ls.bytes));
             want = nb1 >= nb0 ? 1 : 0;
@@ -424,7 +443,7 @@ int finalize(altro_handle_t h)
     }
     h->smem = (int)smem;
     if (!h->kernel) return fail(h, ALTRO_ERR_UNSUPPORTED, "no kernel for this configuration");
-    CK(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(h, raise_smem_limit(h->kernel, (int)smem));
     cudaFuncAttributes fa;
     CK(h, cudaFuncGetAttributes(&fa, h->kernel));
     h->regs = fa.numRegs;
@@ -488,6 +507,7 @@ int altro_default_options(altro_opts_t *o)
     o->reset_penalties = 1;
     o->kickout_max_penalty = 0;
     o->dj_zero_converges = 1;
+    o->first_step_unconditional = 1;
     o->soc_hess_exact = 1;
     o->soc_viol_proj = 1;
     return ALTRO_OK;
@@ -574,6 +594,9 @@ int altro_set_options(altro_handle_t h, const altro_opts_t *o)
     if (!o) return fail(h, ALTRO_ERR_INVALID, "null options");
     if (o->iterations_outer < 1 || o->iterations_inner < 1 || !(o->penalty_initial > 0.0))
         return fail(h, ALTRO_ERR_INVALID, "bad option values");
+    if (!o->reset_penalties)
+        return fail(h, ALTRO_ERR_UNSUPPORTED, "reset_penalties = false is not supported: penalties are not kept across "
+                                              "solves (every benchmark of the reference leaves the default, true)");
     h->opts = *o;
     return ALTRO_OK;
 }
@@ -916,7 +939,9 @@ int altro_solve(altro_handle_t h)
     int rc = finalize(h);
     if (rc) return rc;
     if (!h->have_x0) return fail(h, ALTRO_ERR_STATE, "x0 not set");
-    return launch_solve(h, 0, 0);
+    rc = launch_solve(h, 0, 0);
+    if (!rc) { h->last_run_steps = 0; h->pending_transition = false; }
+    return rc;
 }
 
 int altro_mpc_run(altro_handle_t h, int steps, int shift)
@@ -925,10 +950,14 @@ int altro_mpc_run(altro_handle_t h, int steps, int shift)
     int rc = finalize(h);
     if (rc) return rc;
     if (steps < 1) return fail(h, ALTRO_ERR_INVALID, "steps must be >= 1");
+    if (h->pending_transition)  // the run's first transition takes x0 from X[1]: after altro_mpc_transition that would skip a state
+        return fail(h, ALTRO_ERR_STATE, "altro_mpc_run after altro_mpc_transition: call altro_solve first");
     rc = ensure_stat_capacity(h, steps);
     if (rc) return rc;
     h->have_x0 = true;
-    return launch_solve(h, steps, shift);
+    rc = launch_solve(h, steps, shift);
+    if (!rc) h->last_run_steps = steps;
+    return rc;
 }
 
 int altro_reserve_steps(altro_handle_t h, int steps)
@@ -945,7 +974,7 @@ int altro_get_run_results(altro_handle_t h, int steps, int *iterations, int *ite
                           long long *t_ns)
 {
     REQ(h);
-    if (steps < 1 || steps > h->stat_cap) return fail(h, ALTRO_ERR_INVALID, "steps exceeds the last run");
+    if (steps < 1 || steps > h->last_run_steps) return fail(h, ALTRO_ERR_INVALID, "steps exceeds the last closed-loop run");
     const size_t cnt = (size_t)steps * h->B;
     int rc = ALTRO_OK;
     if (iterations) rc |= download(h, iterations, h->iters, cnt * sizeof(int));
@@ -974,15 +1003,16 @@ int altro_get_stats(altro_handle_t h, int *iterations, int *iterations_outer, in
 {
     REQ(h);
     const size_t B = h->B;
+    const size_t at = h->last_run_steps > 0 ? (size_t)(h->last_run_steps - 1) * B : 0;  // after a run: its final solve
     int rc = ALTRO_OK;
-    if (iterations) rc |= download(h, iterations, h->iters, B * sizeof(int));
-    if (iterations_outer) rc |= download(h, iterations_outer, h->outer, B * sizeof(int));
-    if (status) rc |= download(h, status, h->status, B * sizeof(int));
-    if (ls_trials) rc |= download(h, ls_trials, h->trials, B * sizeof(int));
-    if (cost) rc |= download(h, cost, h->cost, B * sizeof(double));
-    if (cost_al) rc |= download(h, cost_al, h->cost_al, B * sizeof(double));
-    if (c_max) rc |= download(h, c_max, h->cmax, B * sizeof(double));
-    if (penalty_max) rc |= download(h, penalty_max, h->penmax, B * sizeof(double));
+    if (iterations) rc |= download(h, iterations, h->iters + at, B * sizeof(int));
+    if (iterations_outer) rc |= download(h, iterations_outer, h->outer + at, B * sizeof(int));
+    if (status) rc |= download(h, status, h->status + at, B * sizeof(int));
+    if (ls_trials) rc |= download(h, ls_trials, h->trials + at, B * sizeof(int));
+    if (cost) rc |= download(h, cost, h->cost + at, B * sizeof(double));
+    if (cost_al) rc |= download(h, cost_al, h->cost_al + at, B * sizeof(double));
+    if (c_max) rc |= download(h, c_max, h->cmax + at, B * sizeof(double));
+    if (penalty_max) rc |= download(h, penalty_max, h->penmax + at, B * sizeof(double));
     if (rc) return ALTRO_ERR_CUDA;
     CK(h, cudaStreamSynchronize(h->stream));
     return ALTRO_OK;
@@ -998,7 +1028,8 @@ int altro_get_timing(altro_handle_t h, double *device_ms, long long *per_instanc
         *device_ms = ms;
     }
     if (per_instance_ns) {
-        int rc = download(h, per_instance_ns, h->t_ns, (size_t)h->B * sizeof(long long));
+        const size_t at = h->last_run_steps > 0 ? (size_t)(h->last_run_steps - 1) * h->B : 0;
+        int rc = download(h, per_instance_ns, h->t_ns + at, (size_t)h->B * sizeof(long long));
         if (rc) return rc;
         CK(h, cudaStreamSynchronize(h->stream));
     }
@@ -1148,6 +1179,7 @@ int altro_mpc_transition(altro_handle_t h, const double *noise, int shift)
                                                      h->x0, h->trackX, h->trackU, h->Nt, h->kidx, h->xref, h->uref);
     CK(h, cudaGetLastError());
     h->have_x0 = true;
+    h->pending_transition = true;
     h->step_abs += 1;
     if (!h->trackX) {  // the transition kernel advances kidx only together with the reference window
         advance_kidx_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->kidx, h->B, 1);

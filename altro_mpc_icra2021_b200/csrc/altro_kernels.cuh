@@ -1338,13 +1338,15 @@ struct Ctx {
         else rollout_open_loop_impl<false>();
     }
 
-    // Closed-loop rollout with step alpha into Xb, Ub. Returns false if a state leaves the box.
+    // Closed-loop rollout with step alpha into Xb, Ub.  Returns 0 if a state leaves the box, 2 if the trial reproduces
+    // (X, U) bit for bit -- every smaller step then does too (|alpha d| is below half an ulp of u at every knot and dx
+    // stays exactly 0), so the line search can stop without rolling them out -- and 1 otherwise.
     template <bool DS>
-    __device__ __forceinline__ bool rollout_alpha_impl(double alpha)
+    __device__ __forceinline__ int rollout_alpha_impl(double alpha)
     {
         for (int i = tid; i < n; i += T) Xb[i] = X[i];
         gsync<T>();
-        double bad = 0.0;
+        double flag = 0.0;  // 2: out of the box, 1: differs from the current trajectory
         for (int k = 0; k < N - 1; ++k) {
             const double *A = DS ? sA : as_global(P.A) + dyn_index(k) * n * n;
             const double *Bm = DS ? sB : as_global(P.Bm) + dyn_index(k) * n * m;
@@ -1354,6 +1356,7 @@ struct Ctx {
                 double acc = fma(alpha, dv[k * m + i], U[k * m + i]);
                 for (int j = 0; j < n; ++j) acc = fma(Kk[i * n + j], Xb[k * n + j] - X[k * n + j], acc);
                 Ub[k * m + i] = acc;
+                if (!(acc == U[k * m + i])) flag = fmax(flag, 1.0);
             }
             gsync<T>();
             for (int i = tid; i < n; i += T) {
@@ -1361,13 +1364,15 @@ struct Ctx {
                 for (int j = 0; j < n; ++j) acc = fma(A[i * n + j], Xb[k * n + j], acc);
                 for (int j = 0; j < m; ++j) acc = fma(Bm[i * m + j], Ub[k * m + j], acc);
                 Xb[(k + 1) * n + i] = acc;
-                if (!(fabs(acc) <= P.o.max_state_value)) bad = 1.0;
+                if (!(fabs(acc) <= P.o.max_state_value)) flag = 2.0;
+                else if (!(acc == X[(k + 1) * n + i])) flag = fmax(flag, 1.0);
             }
             gsync<T>();
         }
-        return gmax<T>(bad, red) == 0.0;
+        const double f = gmax<T>(flag, red);
+        return f == 2.0 ? 0 : (f == 1.0 ? 1 : 2);
     }
-    __device__ bool rollout_alpha(double alpha)
+    __device__ int rollout_alpha(double alpha)
     {
         return P.dyn_in_smem ? rollout_alpha_impl<true>(alpha) : rollout_alpha_impl<false>(alpha);
     }
@@ -1397,7 +1402,7 @@ struct Ctx {
                 break;
             }
             const long long cr = clock64();
-            bool ok = rollout_alpha(alpha);
+            const int ok = rollout_alpha(alpha);
             ph_roll += clock64() - cr;
             ++trials;
             if (!ok) { ++iter; alpha *= 0.5; continue; }
@@ -1408,6 +1413,8 @@ struct Ctx {
             z = expected > 0.0 ? (J_prev - J) / expected : -1.0;
             ++iter;
             alpha *= 0.5;
+            // bit-identical trial: every remaining (smaller) step would reproduce it and fail the same test
+            if (ok == 2) iter = P.o.iterations_linesearch + 1;
         }
         return J;
     }
@@ -1448,7 +1455,7 @@ struct Ctx {
                 for (int q = 0; q < warp; ++q) aw *= 0.5;
                 double ok = 0.0, Jw = 0.0;
                 if (iter + warp <= P.o.iterations_linesearch) {
-                    ok = v.rollout_alpha(aw) ? 1.0 : 0.0;
+                    ok = (double)v.rollout_alpha(aw);  // 0 out of the box, 1 ok, 2 ok and bit-identical to (X, U)
                     if (ok != 0.0) Jw = v.al_cost(v.Xb, v.Ub);
                 }
                 if (lane == 0) { specr[2 * warp] = ok; specr[2 * warp + 1] = Jw; }
@@ -1467,6 +1474,7 @@ struct Ctx {
                 }
                 ++iter;
                 alpha *= 0.5;
+                if (specr[2 * w] == 2.0) iter = P.o.iterations_linesearch + 1;  // see forward_pass
             }
             __syncthreads();
         }
@@ -1585,6 +1593,8 @@ struct Ctx {
             rollout_open_loop();
             double J_prev = al_cost(X, U);
             J = J_prev;
+            // the initial rollout's cost is not a line-search reference (see altro_opts_t)
+            if (o.first_step_unconditional) J_prev = INFINITY;
             ph[0] += clock64() - c0;
 #pragma unroll 1
             for (int it = 0; it < o.iterations_inner; ++it) {

@@ -460,6 +460,9 @@ class SolverOptions:
     dj_zero_converges: bool = True
     soc_hess_exact: bool = True
     soc_viol_proj: bool = True
+    # the initial rollout's cost is not a line-search reference: the first forward pass of every iLQR solve takes
+    # its full step (J_prev = +inf).  Matches the saved grasp statistics of the reference
+    first_step_unconditional: bool = True
     # accepted for API compatibility; this path has no projected-Newton polish / static variant / logging
     projected_newton: bool = False
     static_bp: bool = True

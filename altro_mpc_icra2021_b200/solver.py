@@ -50,7 +50,7 @@ class AltroOpts(C.Structure):
         (k, C.c_int) for k in (
             "iterations", "iterations_inner", "iterations_outer", "iterations_linesearch", "dJ_counter_limit",
             "reset_duals", "reset_penalties", "kickout_max_penalty", "dj_zero_converges", "soc_hess_exact",
-            "soc_viol_proj")]
+            "soc_viol_proj", "first_step_unconditional")]
 
 
 class AltroError(RuntimeError):

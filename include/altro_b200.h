@@ -58,6 +58,10 @@ typedef struct altro_opts_t {
     int dj_zero_converges; /* 1: 0<=dJ<tol converges, 0: 0<dJ<tol */
     int soc_hess_exact;    /* 1: exact projection Hessian, 0: Gauss-Newton */
     int soc_viol_proj;     /* 1: ||c-Pi(c)||_inf, 0: max(0,||v||-t) */
+    int first_step_unconditional; /* 1: the first forward pass of every iLQR solve compares against J_prev = +inf
+                                     (full step always taken, never the converged iteration); 0: against the cost of
+                                     the initial rollout.  Default 1: reproduces the iteration counts and the
+                                     one-rollout-per-iteration timing saved in grasp_benchmark_data.jld2 */
 } altro_opts_t;
 
 /* SolverOptions() defaults. */

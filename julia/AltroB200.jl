@@ -49,6 +49,7 @@ Base.@kwdef mutable struct SolverOptions
     dj_zero_converges::Cint = 1
     soc_hess_exact::Cint = 1
     soc_viol_proj::Cint = 1
+    first_step_unconditional::Cint = 1
 end
 
 check(h, rc) = rc == 0 || error("altro_b200: " * unsafe_string(ccall((:altro_last_error, lib), Cstring, (Ptr{Cvoid},), h)))

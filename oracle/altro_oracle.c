@@ -52,6 +52,7 @@ void orc_default_opts(orc_opts_t *o)
     o->dj_zero_converges = 1;
     o->soc_hess_exact = 1;
     o->soc_viol_proj = 1;
+    o->first_step_unconditional = 1;
 }
 
 int orc_dual_len(const orc_problem_t *pb)
@@ -664,10 +665,12 @@ restart:;
 
 /* ---------------------------------------------------------------- forward pass (A.8) */
 
-/* Closed-loop rollout with step alpha into Xb,Ub; returns 0 if a state leaves the box. */
+/* Closed-loop rollout with step alpha into Xb,Ub; returns 0 if a state leaves the box, 2 if the trial reproduces
+ * the current trajectory bit for bit (every smaller step then does too: |alpha d| is below half an ulp of u at every
+ * knot, so dx stays exactly 0), else 1. */
 static int rollout_alpha(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, double alpha)
 {
-    int n = pb->n, m = pb->m, N = pb->N, ok = 1;
+    int n = pb->n, m = pb->m, N = pb->N, ok = 1, same = 1;
     memcpy(w->Xb, w->X, sizeof(double) * n); /* x0 */
     for (int k = 0; k < N - 1; ++k) {
         const double *A, *Bm, *dd;
@@ -679,15 +682,18 @@ static int rollout_alpha(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, 
             double acc = fma(alpha, dv[i], u[i]);
             for (int j = 0; j < n; ++j) acc = fma(K[i * n + j], xb[j] - x[j], acc);
             ub[i] = acc;
+            if (!(acc == u[i])) same = 0;
         }
         dyn_step(n, m, A, Bm, dd, xb, ub, xb + n);
-        for (int i = 0; i < n; ++i)
+        for (int i = 0; i < n; ++i) {
             if (!(fabs(xb[n + i]) <= o->max_state_value)) ok = 0;
+            if (!(xb[n + i] == x[n + i])) same = 0;
+        }
     }
-    return ok;
+    return ok ? (same ? 2 : 1) : 0;
 }
 
-/* Returns the accepted cost J; *trials counts rollouts tried. */
+/* Returns the accepted cost J; *trials counts the rollouts evaluated. */
 static double forward_pass(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w, int inst, const double *lam,
                            const double dV[2], double J_prev, double *rho, double *drho, int *trials)
 {
@@ -712,6 +718,9 @@ static double forward_pass(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
         z = expected > 0.0 ? (J_prev - J) / expected : -1.0;
         ++iter;
         alpha *= 0.5;
+        /* the trial reproduced the current trajectory bit for bit: every remaining (smaller) step would too and
+         * fail the same test, so the search is over -- same result as running them, without the rollouts */
+        if (ok == 2) iter = o->iterations_linesearch + 1;
     }
     return J;
 }
@@ -789,6 +798,10 @@ static void solve_instance(const orc_problem_t *pb, const orc_opts_t *o, ws_t *w
         }
         double J_prev = al_cost(pb, w, inst, w->X, w->U, lam);
         J = J_prev;
+        /* first_step_unconditional: the cost of the initial rollout is not a line-search reference -- the first
+         * forward pass of every iLQR solve compares against +inf, so its full step is always taken and the first
+         * iteration can never be the converged one (see altro_oracle.h and DESIGN.md section 2 for the evidence) */
+        if (o->first_step_unconditional) J_prev = INFINITY;
         for (int it = 0; it < o->iterations_inner; ++it) {
             double dV[2];
             if (backward_pass(pb, o, w, inst, lam, &rho, &drho, dV)) { r->status = ORC_NOT_PD; break; }

@@ -100,6 +100,8 @@ typedef struct {
     int dj_zero_converges;  /* 1: 0<=dJ<tol converges (default), 0: 0<dJ<tol */
     int soc_hess_exact;     /* 1: mu*G'*dPi*G (= incl. second-order projection term), 0: Gauss-Newton dPi'dPi */
     int soc_viol_proj;      /* 1: ||c-Pi(c)||_inf, 0: max(0,||v||-t) */
+    int first_step_unconditional; /* 1: J_prev = +inf at the first iteration of every iLQR solve (default), 0: the
+                                     initial rollout's cost (Appendix A.6 as recollected) */
 } orc_opts_t;
 
 void orc_default_opts(orc_opts_t *o);

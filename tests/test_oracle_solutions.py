@@ -178,6 +178,89 @@ def test_random_linear_iteration_statistics_match_reference_data():
     assert np.mean(its == 2) >= 0.92 and its.min() >= 2 and its.max() <= 5, np.bincount(its)
 
 
+def _reference_stats():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_stats.json")) as f:
+        return json.load(f)
+
+
+def _grasp_mpc_iterations(N_mpc, runs, opts, seed):
+    """run_grasp_mpc (grasp_mpc.jl:47-99): every run starts at the beginning of the cold-solved track and takes
+    251 - N_mpc warm-started steps with 1 % noise (grasp_mpc_helpers.jl:9-11)."""
+    from altro_mpc_icra2021_b200.problems import grasp
+    cold = grasp.cold_problem()
+    rc = OracleProblem(cold).solve(grasp.cold_options())
+    assert rc.status[0] == 1
+    Xt, Ut = rc.X[0], rc.U[0]
+    pm = mpc.gen_tracking_problem(cold, Xt, Ut, N_mpc, Qk=1e3, Rk=1.0, Qfk=10.0, batch=runs,
+                                  k_start=np.zeros(runs, np.int64))
+    op = OracleProblem(pm)
+    assert np.all(op.solve(opts, nthreads=4).status == 1)
+    steps = 251 - N_mpc
+    noise = mpc.rng_for(seed, N_mpc).standard_normal((steps, runs, 6))
+    out = op.mpc_run(opts, steps, noise, (1, 0.01, 0.0), (Xt, Ut), None, True, nthreads=4)
+    return out
+
+
+def test_grasp_iteration_statistics_match_reference_data():
+    """The reference's saved runs of the real Altro.jl on the grasp family (grasp_benchmark_data.jld2, 15 runs,
+    3300 warm-started solves, recovered by tests/golden/extract_reference_stats.py): mean 3.31-4.01 per run, median 3,
+    min 2, max 8-20.  Same options (grasp_benchmark.jl:26-34), same horizons, same number of steps, 3 runs each."""
+    from altro_mpc_icra2021_b200.problems import grasp
+    ref = _reference_stats()["grasp"]
+    ref_all = np.concatenate([r["iterations"] for r in ref])
+    ref_hist = np.bincount(ref_all, minlength=64)[:64] / ref_all.size
+    assert ref_all.size == 3300 and ref_all.min() == 2 and ref_all.max() == 20 and np.median(ref_all) == 3
+    ours, means = [], []
+    for N_mpc in (11, 21, 31, 41, 51):
+        out = _grasp_mpc_iterations(N_mpc, 3, grasp.mpc_options(), seed=0xA1720 + 5)
+        assert np.all(out["status"] == 1)  # the reference aborts on anything else (random_linear_problem.jl:166-170)
+        it = out["iterations"]
+        ours.append(it.ravel())
+        means += list(it.mean(axis=0))
+    ours = np.concatenate(ours)
+    hist = np.bincount(ours, minlength=64)[:64] / ours.size
+    assert ours.size == 3300
+    assert 3.2 <= ours.mean() <= 4.1, ours.mean()                     # reference, pooled: 3.648
+    assert min(means) >= 3.0 and max(means) <= 4.3, means             # reference, per run: 3.31 .. 4.01
+    assert np.median(ours) == 3 and ours.min() == 2
+    assert np.mean(ours > 20) <= 0.003, np.sort(ours)[-10:]           # reference: none of 3300 above 20
+    assert np.mean(ours >= 8) <= 0.04                                  # reference: 2.0 %
+    assert np.abs(hist - ref_hist).sum() <= 0.15, np.round(hist[:10], 3)  # L1 distance of the two histograms
+
+
+def test_grasp_statistics_reject_the_line_searched_first_iteration():
+    """The switch that decides the pin: with the cost of the initial rollout as the first line-search reference
+    (Appendix A.6 as recollected) the same runs take 5.5-6.5 iterations on average with maxima of 50-100."""
+    from altro_mpc_icra2021_b200.problems import grasp
+    opts = grasp.mpc_options()
+    opts.first_step_unconditional = False
+    it = _grasp_mpc_iterations(21, 3, opts, seed=0xA1720 + 5)["iterations"]
+    assert it.mean() > 5.0 and np.median(it) >= 4 and it.max() > 25
+
+
+def test_random_linear_iteration_structure_matches_reference_data():
+    """Saved reference runs of the random-linear sweeps (17 sweep points x 100 steps): never a 1, 2 in 92-100 % of
+    the steps of all but one sweep point, and -- every iLQR solve taking at least two iterations because its first
+    one can never be the converged one -- a solve with two outer loops never takes 3."""
+    ref = _reference_stats()["random_linear"]
+    pts = [np.array(r["iterations"]) for rows in ref.values() for r in rows]
+    assert len(pts) == 17 and min(p.min() for p in pts) == 2
+    assert sum(np.mean(p == 2) >= 0.92 for p in pts) == 16
+    assert sum(int(np.sum(np.array(r["iterations"]) == 3)) for r in ref["horizon_comp"]) == 0
+    pm, X, U, ks = random_linear.mpc_problem(12, 6, 21, batch=8)
+    opts = random_linear.mpc_options()
+    op = OracleProblem(pm)
+    op.solve(opts, nthreads=4)
+    noise = mpc.rng_for(3, 7).standard_normal((100, 8, 12))
+    out = op.mpc_run(opts, 100, noise, (1, 0.01, 0.0), (X, U), None, True, nthreads=4)
+    it, ou = out["iterations"], out["iterations_outer"]
+    assert np.all(out["status"] == 1) and it.min() == 2
+    assert np.all(it >= 2 * ou)  # two iterations per outer loop at least
+    assert np.mean(it == 2) >= 0.80 and it.max() <= 10, np.bincount(it.ravel())
+
+
 @pytest.mark.parametrize("family", ["quadruped_lin", "quadruped_soc", "flexsat"])
 def test_families_converge_and_are_feasible(family):
     if family == "flexsat":
