@@ -15,7 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "altro_kernels.cuh"
+#include "altro_lane.cuh"
 
 using namespace altro;
 
@@ -84,6 +84,13 @@ struct altro_handle_s {
     const void *kernel = nullptr;
     Layout lay;
     int spec = 0, spec_req = -1;  // speculative line search: in use / requested (-1 = automatic)
+    // lane-per-instance kernel (altro_lane.cuh): small dimensions, one thread per instance
+    int kernel_mode = 0;  // 0 automatic, 1 CTA per instance, 2 lane per instance
+    const void *lane_kern = nullptr;
+    LaneLayout lane_lay{};
+    double *lane_ws = nullptr;
+    size_t lane_stride = 0;
+    int lane_smem = 0, lane_regs = 0;
 };
 
 namespace {
@@ -265,6 +272,7 @@ const void *kernel_6_6(int T);    // grasp
 const void *kernel_12_3(int T);   // flexible satellite
 const void *kernel_12_6(int T);   // random linear (default)
 const void *kernel_0_0(int T);    // run-time dimensions
+const void *lane_kernel(int n, int m);  // lane-per-instance kernels (6, 3), (6, 6)
 }  // namespace altro
 
 namespace {
@@ -450,6 +458,26 @@ int finalize(altro_handle_t h)
     int nb = 0;
     CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, h->kernel, T, smem));
     h->ctas_per_sm = nb;
+    // lane-per-instance kernel for the small-dimension families, unless the caller asked for a CTA geometry
+    h->lane_kern = nullptr;
+    {
+        int mode = h->kernel_mode;
+        if (const char *e = getenv("ALTRO_B200_LANE")) mode = atoi(e) ? 2 : 1;
+        const void *lk = lane_kernel(n, m);
+        if (mode == 2 && !lk) return fail(h, ALTRO_ERR_UNSUPPORTED, "no lane-per-instance kernel for these dimensions");
+        // automatic: batches of at least two warps (a lone instance is served faster by a whole CTA)
+        if (lk && mode != 1 && (mode == 2 || (B >= 64 && h->threads_req == 0 && !getenv("ALTRO_B200_THREADS") && !getenv("ALTRO_B200_GENERIC")))) {
+            h->lane_lay = make_lane_layout(n, m, N, P);
+            h->lane_stride = ((size_t)B + 31) / 32 * 32;
+            CK(h, dalloc(&h->lane_ws, (size_t)h->lane_lay.total * h->lane_stride));
+            h->lane_smem = LANE_SCRATCH * 32 * (int)sizeof(double);
+            CK(h, raise_smem_limit(lk, h->lane_smem));
+            cudaFuncAttributes la;
+            CK(h, cudaFuncGetAttributes(&la, lk));
+            h->lane_regs = la.numRegs;
+            h->lane_kern = lk;
+        }
+    }
     h->finalized = true;
     return ALTRO_OK;
 }
@@ -562,7 +590,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->x0_snap, h->xref_snap, h->uref_snap, h->kidx_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->ws, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->ws, h->lane_ws, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -923,7 +951,12 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     if (h->trace)
         CK(h, cudaMemsetAsync(h->trace, 0, (size_t)h->B * h->trace_rows * TRACE_COLS * sizeof(double), h->stream));
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    CK(h, cudaLaunchKernel(h->kernel, dim3(h->B), dim3(h->threads), args, (size_t)h->smem, h->stream));
+    if (h->lane_kern && !h->trace && !h->phase) {  // (the per-iteration trace and the phase counters are CTA-kernel features)
+        void *largs[] = {&P, &h->lane_lay, &h->lane_ws, &h->lane_stride};
+        CK(h, cudaLaunchKernel(h->lane_kern, dim3((h->B + 31) / 32), dim3(32), largs, (size_t)h->lane_smem, h->stream));
+    } else {
+        CK(h, cudaLaunchKernel(h->kernel, dim3(h->B), dim3(h->threads), args, (size_t)h->smem, h->stream));
+    }
     CK(h, cudaEventRecord(h->ev1, h->stream));
     h->step_abs += steps;
     if (steps > 0) {
@@ -1210,6 +1243,26 @@ int altro_set_launch_config(altro_handle_t h, int threads)
     if (threads != 0 && threads != 32 && threads != 64 && threads != 128 && threads != 256)
         return fail(h, ALTRO_ERR_INVALID, "threads per instance must be 0 (auto), 32, 64, 128 or 256");
     h->threads_req = threads;
+    return ALTRO_OK;
+}
+
+int altro_set_kernel_mode(altro_handle_t h, int mode)
+{
+    REQ(h);
+    if (h->finalized) return fail(h, ALTRO_ERR_STATE, "launch configuration is fixed after the first solve");
+    if (mode < 0 || mode > 2) return fail(h, ALTRO_ERR_INVALID, "kernel mode must be 0 (auto), 1 (CTA per instance) or 2 (lane per instance)");
+    h->kernel_mode = mode;
+    return ALTRO_OK;
+}
+
+int altro_get_kernel_mode(altro_handle_t h, int *mode, int *lane_regs, int *lane_smem)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (mode) *mode = h->lane_kern ? 2 : 1;
+    if (lane_regs) *lane_regs = h->lane_regs;
+    if (lane_smem) *lane_smem = h->lane_smem;
     return ALTRO_OK;
 }
 

@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "altro_get_run_results",
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
     "altro_set_line_search_mode", "altro_get_line_search_mode", "altro_reserve_steps",
+    "altro_set_kernel_mode", "altro_get_kernel_mode",
     "altro_measure_peaks",
 ]
 
@@ -109,7 +110,7 @@ class SolverStats:
 class ALTROSolver:
     def __init__(self, prob: Problem, opts: Optional[SolverOptions] = None, device: int = 0,
                  threads_per_instance: int = 0, stream: Optional[int] = None, pin: bool = False,
-                 speculative_line_search: Optional[bool] = None, **kwargs):
+                 speculative_line_search: Optional[bool] = None, kernel: str = "auto", **kwargs):
         self.lib = load_library()
         self.prob = prob
         self.opts = (opts or SolverOptions()).copy()
@@ -126,6 +127,8 @@ class ALTROSolver:
             self._ck(self.lib.altro_set_launch_config(self.h, threads_per_instance))
         if speculative_line_search is not None:
             self._ck(self.lib.altro_set_line_search_mode(self.h, int(bool(speculative_line_search))))
+        if kernel != "auto":  # "cta": one CTA per instance, "lane": one thread per instance (small dimensions)
+            self._ck(self.lib.altro_set_kernel_mode(self.h, {"cta": 1, "lane": 2}[kernel]))
         self._ck(self.lib.altro_set_cost_diag(self.h, _p(prob.obj.Q), _p(prob.obj.R), _p(prob.obj.Qf)))
         for c in prob.constraints.flat:
             cid = C.c_int()
@@ -393,6 +396,11 @@ class ALTROSolver:
         spec = C.c_int()
         self._ck(self.lib.altro_get_line_search_mode(self.h, C.byref(spec)))
         info["speculative_line_search"] = bool(spec.value)
+        km, lr, lsm = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.altro_get_kernel_mode(self.h, C.byref(km), C.byref(lr), C.byref(lsm)))
+        info["kernel"] = "lane" if km.value == 2 else "cta"
+        if km.value == 2:
+            info.update(lane_regs_per_thread=lr.value, lane_smem_bytes=lsm.value, instances_per_warp=32)
         return info
 
     def all_succeeded(self) -> bool:

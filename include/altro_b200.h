@@ -200,6 +200,11 @@ int altro_host_unregister(void *ptr);
 /* Launch geometry of the solve kernel: threads per instance, dynamic shared memory bytes per
  * instance (CTA), registers per thread, resident CTAs per SM. threads=0 in the setter = automatic. */
 int altro_set_launch_config(altro_handle_t h, int threads_per_instance);
+/* Which kernel runs solve!: 1 = one CTA per instance (any dimensions), 2 = one thread per instance, a warp advancing
+ * 32 instances (small dimensions: rocket 6/3, grasp 6/6), 0 = automatic (lane kernel where one exists, unless a CTA
+ * geometry was asked for).  Results are bit-identical either way.  The getter reports the kernel in use. */
+int altro_set_kernel_mode(altro_handle_t h, int mode);
+int altro_get_kernel_mode(altro_handle_t h, int *mode, int *lane_regs_per_thread, int *lane_smem_bytes);
 int altro_get_launch_info(altro_handle_t h, int *threads_per_instance, int *smem_bytes, int *regs_per_thread,
                           int *ctas_per_sm, int *num_sms);
 

@@ -60,7 +60,7 @@ def test_rocket_4096_properties():
     for st in range(3):
         g.solve()
         s = g.stats
-        assert np.mean(s.status == 1) > 0.995
+        assert np.all(s.status == 1), np.bincount(s.status)  # the reference aborts a sweep on anything else
         ok = s.status == 1
         assert np.all(s.c_max[ok] < opts.constraint_tolerance)
         U, X = prob.U[ok], prob.X[ok]
