@@ -85,12 +85,15 @@ struct altro_handle_s {
     Layout lay;
     int spec = 0, spec_req = -1;  // speculative line search: in use / requested (-1 = automatic)
     // lane-per-instance kernel (altro_lane.cuh): small dimensions, one thread per instance
+    int run_chunk = 1;    // closed-loop runs: steps per work item of the persistent grid (0 = one CTA per instance)
+    int *q_ctrl = nullptr;  // [2 + B]: queue head, error flag, per-instance completed steps
     int kernel_mode = 0;  // 0 automatic, 1 CTA per instance, 2 lane per instance
     const void *lane_kern = nullptr;
     LaneLayout lane_lay{};
     double *lane_ws = nullptr;
     size_t lane_stride = 0;
-    int lane_smem = 0, lane_regs = 0;
+    int lane_smem = 0, lane_regs = 0, lane_lpw = 8, lane_scratch = 0;
+    std::vector<double> hA, hB, hd, hQ, hR, hQf;  // host copies (shared LTI model, weights): lane-kernel parameters
 };
 
 namespace {
@@ -272,7 +275,8 @@ const void *kernel_6_6(int T);    // grasp
 const void *kernel_12_3(int T);   // flexible satellite
 const void *kernel_12_6(int T);   // random linear (default)
 const void *kernel_0_0(int T);    // run-time dimensions
-const void *lane_kernel(int n, int m);  // lane-per-instance kernels (6, 3), (6, 6)
+bool lane_supported(int n, int m);  // lane-per-instance kernels (6, 3), (6, 6)
+cudaError_t lane_launch(int n, int m, const LaneLaunch &a);
 }  // namespace altro
 
 namespace {
@@ -458,19 +462,32 @@ int finalize(altro_handle_t h)
     int nb = 0;
     CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, h->kernel, T, smem));
     h->ctas_per_sm = nb;
-    // lane-per-instance kernel for the small-dimension families, unless the caller asked for a CTA geometry
+    // lane-per-instance kernel for the small-dimension families (shared LTI model), unless the caller asked for a CTA
+    // geometry
     h->lane_kern = nullptr;
     {
         int mode = h->kernel_mode;
         if (const char *e = getenv("ALTRO_B200_LANE")) mode = atoi(e) ? 2 : 1;
-        const void *lk = lane_kernel(n, m);
-        if (mode == 2 && !lk) return fail(h, ALTRO_ERR_UNSUPPORTED, "no lane-per-instance kernel for these dimensions");
-        // automatic: batches of at least two warps (a lone instance is served faster by a whole CTA)
-        if (lk && mode != 1 && (mode == 2 || (B >= 64 && h->threads_req == 0 && !getenv("ALTRO_B200_THREADS") && !getenv("ALTRO_B200_GENERIC")))) {
+        const bool can = lane_supported(n, m) && h->dyn_in_smem && h->hA.size() == (size_t)n * n;
+        if (mode == 2 && !can) return fail(h, ALTRO_ERR_UNSUPPORTED, "no lane-per-instance kernel for these dimensions / this dynamics layout");
+        // opt-in only: measured 10x slower than the CTA kernel on the 4096-instance batches (see altro_lane.cuh)
+        if (can && mode == 2) {
+            h->lane_lpw = 8;
+            if (const char *e = getenv("ALTRO_B200_LPW")) h->lane_lpw = atoi(e);
+            if (h->lane_lpw != 8 && h->lane_lpw != 32)
+                return fail(h, ALTRO_ERR_INVALID, "instances per warp must be 8 or 32");
             h->lane_lay = make_lane_layout(n, m, N, P);
             h->lane_stride = ((size_t)B + 31) / 32 * 32;
             CK(h, dalloc(&h->lane_ws, (size_t)h->lane_lay.total * h->lane_stride));
-            h->lane_smem = LANE_SCRATCH * 32 * (int)sizeof(double);
+            h->lane_scratch = LANE_SCRATCH + N * (1 + ncons);
+            h->lane_smem = (int)((size_t)std::max(ncons, 1) * sizeof(ConDesc) + (size_t)h->lane_scratch * h->lane_lpw * sizeof(double));
+            if ((size_t)h->lane_smem > limit) return fail(h, ALTRO_ERR_UNSUPPORTED, "lane kernel scratch exceeds shared memory");
+            LaneLaunch q{};
+            q.lpw = h->lane_lpw;
+            q.A = q.B = q.d = q.Q = q.R = q.Qf = h->hA.data();  // only resolving the kernel: contents unused
+            const void *lk = nullptr;
+            q.query = &lk;
+            CK(h, lane_launch(n, m, q));
             CK(h, raise_smem_limit(lk, h->lane_smem));
             cudaFuncAttributes la;
             CK(h, cudaFuncGetAttributes(&la, lk));
@@ -590,7 +607,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->x0_snap, h->xref_snap, h->uref_snap, h->kidx_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->ws, h->lane_ws, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->ws, h->lane_ws, h->q_ctrl, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -649,6 +666,14 @@ int altro_set_dynamics(altro_handle_t h, int per_knot, int per_instance, const d
         h->dyn_count = cnt; h->dyn_per_knot = per_knot; h->dyn_per_instance = per_instance;
         h->have_dyn = true;
     }
+    if (cnt == 1) {  // shared LTI model: host copy for the lane kernel's constant parameters
+        h->hA.assign(A, A + n * n);
+        h->hB.assign(Bm, Bm + n * m);
+        if (d) h->hd.assign(d, d + n);
+        else h->hd.assign(n, 0.0);
+    } else {
+        h->hA.clear();
+    }
     int rc = upload(h, h->A, A, cnt * n * n);
     if (rc) return rc;
     rc = upload(h, h->Bm, Bm, cnt * n * m);
@@ -697,6 +722,9 @@ int altro_set_cost_diag(altro_handle_t h, const double *Q, const double *R, cons
     if (!Q || !R || !Qf) return fail(h, ALTRO_ERR_INVALID, "null weights");
     for (int i = 0; i < h->m; ++i)
         if (!(R[i] > 0.0)) return fail(h, ALTRO_ERR_INVALID, "R must be positive");
+    h->hQ.assign(Q, Q + h->n);
+    h->hR.assign(R, R + h->m);
+    h->hQf.assign(Qf, Qf + h->n);
     int rc = upload(h, h->Q, Q, h->n);
     if (!rc) rc = upload(h, h->R, R, h->m);
     if (!rc) rc = upload(h, h->Qf, Qf, h->n);
@@ -948,14 +976,31 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     P.phase = h->phase;
     P.phase_detail = getenv("ALTRO_B200_PHASE_DETAIL") ? 1 : 0;
     void *args[] = {&P};
+    // closed-loop runs of the shared-memory-resident CTA kernels go through the persistent grid + work queue
+    int chunk = h->run_chunk;
+    if (const char *e = getenv("ALTRO_B200_QUEUE")) chunk = atoi(e);
+    const bool lane = h->lane_kern && !h->trace && !h->phase;
+    const bool queued = steps > 0 && chunk > 0 && !lane && h->threads > 32 && !h->lay.big && !h->trace &&
+                        (long long)h->B * ((steps + chunk - 1) / chunk) < (1ll << 31);
+    int grid = h->B;
+    if (queued) {
+        if (!h->q_ctrl) CK(h, dalloc(&h->q_ctrl, (size_t)h->B + 2));
+        CK(h, cudaMemsetAsync(h->q_ctrl, 0, ((size_t)h->B + 2) * sizeof(int), h->stream));
+        P.q_chunk = chunk; P.q_head = h->q_ctrl; P.q_error = h->q_ctrl + 1; P.q_done = h->q_ctrl + 2;
+        grid = std::min(h->B, std::max(1, h->ctas_per_sm) * h->num_sms);
+    }
     if (h->trace)
         CK(h, cudaMemsetAsync(h->trace, 0, (size_t)h->B * h->trace_rows * TRACE_COLS * sizeof(double), h->stream));
     CK(h, cudaEventRecord(h->ev0, h->stream));
-    if (h->lane_kern && !h->trace && !h->phase) {  // (the per-iteration trace and the phase counters are CTA-kernel features)
-        void *largs[] = {&P, &h->lane_lay, &h->lane_ws, &h->lane_stride};
-        CK(h, cudaLaunchKernel(h->lane_kern, dim3((h->B + 31) / 32), dim3(32), largs, (size_t)h->lane_smem, h->stream));
+    if (lane) {  // (the per-iteration trace and the phase counters are CTA-kernel features)
+        LaneLaunch a{};
+        a.P = &P;
+        a.A = h->hA.data(); a.B = h->hB.data(); a.d = h->hd.data(); a.Q = h->hQ.data(); a.R = h->hR.data(); a.Qf = h->hQf.data();
+        a.L = h->lane_lay; a.ws = h->lane_ws; a.stride = h->lane_stride; a.lpw = h->lane_lpw;
+        a.scratch_per_lane = h->lane_scratch; a.smem = (size_t)h->lane_smem; a.stream = h->stream;
+        CK(h, lane_launch(h->n, h->m, a));
     } else {
-        CK(h, cudaLaunchKernel(h->kernel, dim3(h->B), dim3(h->threads), args, (size_t)h->smem, h->stream));
+        CK(h, cudaLaunchKernel(h->kernel, dim3(grid), dim3(h->threads), args, (size_t)h->smem, h->stream));
     }
     CK(h, cudaEventRecord(h->ev1, h->stream));
     h->step_abs += steps;
@@ -1008,6 +1053,12 @@ int altro_get_run_results(altro_handle_t h, int steps, int *iterations, int *ite
 {
     REQ(h);
     if (steps < 1 || steps > h->last_run_steps) return fail(h, ALTRO_ERR_INVALID, "steps exceeds the last closed-loop run");
+    if (h->q_ctrl) {
+        int qerr = 0;
+        CK(h, cudaMemcpyAsync(&qerr, h->q_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (qerr) return fail(h, ALTRO_ERR_CUDA, "closed-loop run: a work item waited too long for its predecessor (run aborted)");
+    }
     const size_t cnt = (size_t)steps * h->B;
     int rc = ALTRO_OK;
     if (iterations) rc |= download(h, iterations, h->iters, cnt * sizeof(int));
@@ -1246,6 +1297,14 @@ int altro_set_launch_config(altro_handle_t h, int threads)
     return ALTRO_OK;
 }
 
+int altro_set_run_queue(altro_handle_t h, int steps_per_item)
+{
+    REQ(h);
+    if (steps_per_item < 0) return fail(h, ALTRO_ERR_INVALID, "steps per work item must be >= 0 (0 = one CTA per instance)");
+    h->run_chunk = steps_per_item;
+    return ALTRO_OK;
+}
+
 int altro_set_kernel_mode(altro_handle_t h, int mode)
 {
     REQ(h);
@@ -1255,12 +1314,13 @@ int altro_set_kernel_mode(altro_handle_t h, int mode)
     return ALTRO_OK;
 }
 
-int altro_get_kernel_mode(altro_handle_t h, int *mode, int *lane_regs, int *lane_smem)
+int altro_get_kernel_mode(altro_handle_t h, int *mode, int *lane_regs, int *lane_smem, int *lpw)
 {
     REQ(h);
     int rc = finalize(h);
     if (rc) return rc;
     if (mode) *mode = h->lane_kern ? 2 : 1;
+    if (lpw) *lpw = h->lane_lpw;
     if (lane_regs) *lane_regs = h->lane_regs;
     if (lane_smem) *lane_smem = h->lane_smem;
     return ALTRO_OK;

@@ -166,6 +166,10 @@ struct Params {
     double *ws;       // large state dimension: per-instance workspace [B][lay.ws_doubles]
     Layout lay;
     int spec;  // line-search trials evaluated concurrently, one per warp (0 = sequential)
+    // closed-loop runs on a persistent grid: work items (instance, chunk of `q_chunk` steps) are handed out chunk-major
+    // from q_head; q_done[inst] = number of steps of the instance that are complete and stored (see Ctx::solve_queued)
+    int q_chunk;
+    int *q_head, *q_done, *q_error;
     altro_opts_t o;
 };
 
@@ -363,6 +367,22 @@ struct Ctx {
         set_step(0);
     }
 
+    // (re)binds the context to instance i: persistent CTAs walk over many instances
+    __device__ __forceinline__ void bind(int i)
+    {
+        inst = i + P.inst_offset;
+        dyn_base = P.dyn_per_instance ? (size_t)inst * (P.dyn_sched ? (size_t)P.dyn_slots : (P.dyn_per_knot ? (size_t)(N - 1) : 1)) : 0;
+        kcur = P.kidx ? P.kidx[inst] : 0;
+        if constexpr (!ALL_SMEM) {
+            if (!P.ref_in_smem) {
+                xr = P.xref + (size_t)inst * N * n;
+                ur = P.uref + (size_t)inst * (N - 1) * m;
+            }
+            if (P.ex_glob) ex = P.ex_glob + (size_t)inst * P.EX;
+        }
+        set_step(0);
+    }
+
     __device__ __forceinline__ void set_step(int st)
     {
         if (P.dyn_sched) sched = P.dyn_sched + (size_t)inst * P.sched_len + min(P.step0 + st, P.sched_len - N);
@@ -391,7 +411,9 @@ struct Ctx {
     }
 
     // ---------------------------------------------------------------- load / store
-    __device__ void load()
+    // Everything that does not depend on the instance: weights, shared LTI model, descriptors, gather tables, the cost
+    // Hessian entries no block touches.
+    __device__ void load_static()
     {
 #pragma unroll 1
         for (int i = tid; i < n; i += T) { Qd[i] = P.Q[i]; Qfd[i] = P.Qf[i]; }
@@ -405,31 +427,6 @@ struct Ctx {
 #pragma unroll 1
             for (int i = tid; i < n; i += T) sd[i] = P.d[i];
         }
-        if (P.steps > 0) {  // closed-loop run: start from the previous solution (its x_1 is the next x_0)
-            const double *gX = P.X + (size_t)inst * N * n;
-#pragma unroll 1
-            for (int i = tid; i < N * n; i += T) X[i] = gX[i];
-        } else {
-            const double *gx0 = P.x0 + (size_t)inst * n;
-#pragma unroll 1
-            for (int i = tid; i < n; i += T) X[i] = gx0[i];
-        }
-        const double *gU = P.U + (size_t)inst * (N - 1) * m;
-#pragma unroll 1
-        for (int i = tid; i < (N - 1) * m; i += T) U[i] = gU[i];
-        const double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
-        if (ALL_SMEM || P.ref_in_smem) {
-#pragma unroll 1
-            for (int i = tid; i < N * n; i += T) xr[i] = gxr[i];
-#pragma unroll 1
-            for (int i = tid; i < (N - 1) * m; i += T) ur[i] = gur[i];
-        }
-        const double *gl = P.lam + (size_t)inst * P.P;
-        const bool rd = P.o.reset_duals != 0;
-#pragma unroll 1
-        for (int i = tid; i < P.P; i += T) lam[i] = rd ? 0.0 : gl[i];
-#pragma unroll 1
-        for (int i = tid; i < MAX_CON; i += T) mu[i] = P.o.penalty_initial;
         const int words = ncon * (int)(sizeof(ConDesc) / sizeof(int));
         const int *src = reinterpret_cast<const int *>(P.con);
         int *dst = reinterpret_cast<int *>(cd);
@@ -445,6 +442,45 @@ struct Ctx {
             else if (t >= n + n * n + m) { const int e = t - (n + n * n + m), i = e / m, j = e - i * m; base = (i == j) ? P.dt * P.R[i] : 0.0; }
             Qi[t] = base;
         }
+    }
+
+    // The instance's state: warm start, duals, reference window.  CG = true reads through L2 (ld.global.cg): in a queued
+    // run another SM wrote these rows a moment ago and this SM's L1 may still hold an older copy.
+    template <bool CG>
+    __device__ void load_state()
+    {
+        auto rd_ = [](const double *p) { return CG ? __ldcg(p) : *p; };
+        if (P.steps > 0) {  // closed-loop run: start from the previous solution (its x_1 is the next x_0)
+            const double *gX = P.X + (size_t)inst * N * n;
+#pragma unroll 1
+            for (int i = tid; i < N * n; i += T) X[i] = rd_(gX + i);
+        } else {
+            const double *gx0 = P.x0 + (size_t)inst * n;
+#pragma unroll 1
+            for (int i = tid; i < n; i += T) X[i] = gx0[i];
+        }
+        const double *gU = P.U + (size_t)inst * (N - 1) * m;
+#pragma unroll 1
+        for (int i = tid; i < (N - 1) * m; i += T) U[i] = rd_(gU + i);
+        const double *gxr = P.xref + (size_t)inst * N * n, *gur = P.uref + (size_t)inst * (N - 1) * m;
+        if (ALL_SMEM || P.ref_in_smem) {
+#pragma unroll 1
+            for (int i = tid; i < N * n; i += T) xr[i] = rd_(gxr + i);
+#pragma unroll 1
+            for (int i = tid; i < (N - 1) * m; i += T) ur[i] = rd_(gur + i);
+        }
+        const double *gl = P.lam + (size_t)inst * P.P;
+        const bool rd = P.o.reset_duals != 0;
+#pragma unroll 1
+        for (int i = tid; i < P.P; i += T) lam[i] = rd ? 0.0 : rd_(gl + i);
+#pragma unroll 1
+        for (int i = tid; i < MAX_CON; i += T) mu[i] = P.o.penalty_initial;
+    }
+
+    __device__ void load()
+    {
+        load_static();
+        load_state<false>();
         gsync<T>();
     }
 
@@ -1660,19 +1696,16 @@ struct Ctx {
         }
     }
 
-    __device__ void solve()
+    // steps [s0, s1) of the closed-loop run of the bound instance (or the one plain solve! when P.steps == 0)
+    __device__ void run_steps(int s0, int s1, long long t0)
     {
-        long long t0 = 0;
-        if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        load();
-        const int steps = P.steps > 0 ? P.steps : 1;
 #pragma unroll 1
-        for (int st = 0; st < steps; ++st) {
+        for (int st = s0; st < s1; ++st) {
             if (P.steps > 0) {
                 set_step(st + 1);  // the window moves one knot forward with every transition
                 kcur = (P.kidx ? P.kidx[inst] : 0) + st + 1;
                 transition(st);
-                if (st > 0) {  // every solve! starts from reset penalties (and duals, if asked)
+                if (st > s0) {  // every solve! starts from reset penalties (and duals, if asked); load_state did it for s0
                     if (P.o.reset_duals)
 #pragma unroll 1
                         for (int i = tid; i < P.P; i += T) lam[i] = 0.0;
@@ -1695,7 +1728,64 @@ struct Ctx {
                 t0 = t1v;
             }
         }
+    }
+
+    __device__ void solve()
+    {
+        long long t0 = 0;
+        if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        load();
+        run_steps(0, P.steps > 0 ? P.steps : 1, t0);
         store();
+    }
+
+    // Closed-loop run on a persistent grid (one CTA per resident slot): the CTAs pull (instance, chunk of q_chunk
+    // steps) items from an atomic counter, chunk-major, so that every slot stays busy until the whole batch is done
+    // -- no wave quantisation (4096 instances over 1184 slots = 3.46 waves) and no waiting for the slot that happened
+    // to get the longest chains.  An item needs the instance's previous chunk: it was handed out a whole round (B
+    // items) earlier, so it is normally long finished; otherwise thread 0 waits on q_done[inst].  State travels
+    // through global memory (a few KB per item, L2-resident), written with a release fence and read through L2.
+    __device__ void solve_queued()
+    {
+        load_static();
+        gsync<T>();
+        const int chunk = P.q_chunk, nchunk = (P.steps + chunk - 1) / chunk;
+        const long long total = (long long)nchunk * P.B;
+        for (;;) {
+            if (tid == 0) {
+                const long long t = (long long)atomicAdd(P.q_head, 1);
+                int go = t < total ? 1 : 0;
+                if (go) {
+                    const int i = (int)(t % P.B), c = (int)(t / P.B);
+                    if (c > 0) {  // wait for the instance's previous chunk (bounded: a lost item must not hang the GPU)
+                        const long long w0 = clock64();
+                        while (atomicAdd(P.q_done + i, 0) < c * chunk) {
+                            __nanosleep(256);
+                            if (clock64() - w0 > (1ll << 33)) { atomicExch(P.q_error, 1); go = 0; break; }
+                        }
+                    }
+                    reinterpret_cast<int *>(bc)[0] = i;
+                    reinterpret_cast<int *>(bc)[1] = c;
+                }
+                reinterpret_cast<int *>(bc)[2] = go;
+            }
+            __syncthreads();
+            const int go = reinterpret_cast<int *>(bc)[2], i = reinterpret_cast<int *>(bc)[0], c = reinterpret_cast<int *>(bc)[1];
+            __syncthreads();
+            if (!go) break;
+            __threadfence();  // acquire: the previous chunk's rows are visible before they are read
+            long long t0 = 0;
+            if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            bind(i);
+            load_state<true>();
+            gsync<T>();
+            const int s0 = c * chunk, s1 = min(P.steps, s0 + chunk);
+            run_steps(s0, s1, t0);
+            store();
+            __threadfence();  // release: rows first, then the step count
+            __syncthreads();
+            if (tid == 0) atomicExch(P.q_done + i, s1);
+        }
     }
 };
 
@@ -1709,6 +1799,9 @@ __global__ void __launch_bounds__(T, ((NX == 12 && NU == 12) ? (256 / T > 0 ? 25
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<NX, NU, T> ctx(P, smem_raw);
+    if constexpr (T > 32) {
+        if (P.q_head) { ctx.solve_queued(); return; }
+    }
     ctx.solve();
 }
 

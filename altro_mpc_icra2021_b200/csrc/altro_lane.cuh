@@ -15,6 +15,13 @@
 //   MPC step on its own.  Lanes therefore desynchronise across iterations, outer loops and MPC steps instead
 //   of waiting for the slowest of the 32 at every solve; the dominant phase (backward pass) runs with nearly
 //   all lanes active in every trip.
+// STATUS (measured on B200, profiles/r2_lane_kernel.md): correct (bit-identical) but about 10x SLOWER than the
+// CTA-per-instance kernel on the 4096-instance rocket batch, at every instances-per-warp setting.  With 4096
+// instances per GPU there are only 128 .. 1024 such warps, each a serial instruction stream at 0.07 - 0.15 IPC
+// (long-scoreboard and fixed-latency stalls, 250 k instructions per trip), and time = serial instructions x latency /
+// instances in flight per SM comes out the same whatever the lanes-per-warp split.  Kept as an opt-in alternative
+// (altro_set_kernel_mode(h, 2)) and as the host-testable restatement of the solver; never selected automatically.
+//
 // * Arithmetic is the oracle's, operation for operation (fma chains over ascending index from a stated initial
 //   value, canonical 32-partial cost sums), so results are bit-identical to oracle/altro_oracle.c and to the
 //   CTA kernel.  Everything per-lane is __host__ __device__: tests/native/lane_host.cu runs the same code on
@@ -51,21 +58,63 @@ inline LaneLayout make_lane_layout(int n, int m, int N, int P)
     return l;
 }
 
-constexpr int LANE_SCRATCH = 288;  // per-lane doubles of run-time indexed scratch (see Lane::sc)
+constexpr int LANE_SCRATCH = 304;  // per-lane doubles of run-time indexed scratch, followed by N (1 + ncon) cost items
+
+// Shared LTI model and diagonal weights, passed BY VALUE as a kernel parameter: every use has a compile-time index,
+// so the operands come straight from the constant bank (no load instruction, no register).
+template <int NX, int NU>
+struct LaneConst {
+    double A[NX * NX], B[NX * NU], d[NX], Q[NX], R[NU], Qf[NX];
+};
+
+// Arguments of one lane-kernel launch (host side; see inst_lane.cu).
+struct LaneLaunch {
+    const Params *P;
+    const double *A, *B, *d, *Q, *R, *Qf;  // host copies of the shared LTI model and the diagonal weights
+    LaneLayout L;
+    double *ws;
+    size_t stride;
+    int lpw, scratch_per_lane;
+    size_t smem;
+    cudaStream_t stream;
+    const void **query;  // non-null: only return the kernel's address (for attribute calls), do not launch
+};
+
+template <class Tp>
+ALTRO_HD Tp *lane_global(Tp *p)
+{
+    // (no __builtin_assume(__isGlobal(p)) here: with it nvcc 12.9 generated code that gave wrong results on sm_100a)
+    return p;
+}
+template <class Tp>
+ALTRO_HD Tp *lane_shared(Tp *p)
+{
+    // (see lane_global)
+    return p;
+}
+ALTRO_HD void lane_prefetch(const double *p)
+{
+#if defined(__CUDA_ARCH__) && defined(ALTRO_LANE_PREFETCH)  // measured: 12 % slower with the prefetches than without
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 enum { LP_STEP_BEGIN = 0, LP_OUTER_BEGIN, LP_BP, LP_TRIAL, LP_POST, LP_OUTER_END, LP_STEP_END, LP_DONE };
 
-template <int NX, int NU>
+// SS: stride of the per-lane scratch = lanes per warp that carry an instance (device), 1 on the host.
+template <int NX, int NU, int SS>
 struct Lane {
-    static constexpr int n = NX, m = NU;
+    static constexpr int n = NX, m = NU, ss = SS;
     const Params &P;
+    const LaneConst<NX, NU> &C;
     const LaneLayout L;
-    double *ws;      // element-major workspace, this lane's column: element e at ws[e * stride]
+    double *ws;      // element-major workspace (global memory), this lane's column: element e at ws[e * stride]
     size_t stride;
-    double *scr;     // run-time indexed scratch, element i at scr[i * ss]
-    int ss;
+    double *scr;     // run-time indexed scratch (shared memory), element i at scr[i * SS]
     int inst, N, ncon;
-    const ConDesc *cd;
+    const ConDesc *cd;  // descriptors (staged in shared memory on the device)
     // solver state
     int phase, st, steps, outer, iters, inner_it, trials, status, dJ_zero, ls_iter, kcur;
     double rho, drho, J, J_prev, Jls, dV1, dV2, alpha, z, cmax, pen_max, ctol, gtol;
@@ -83,17 +132,22 @@ struct Lane {
     static constexpr int SC_D = 136;   // D / q   [8]
     static constexpr int SC_EX = 144;  // state side of the knot in flight:   [Qx (8) | Qxx (8 x 8)]
     static constexpr int SC_EU = 216;  // control side of the knot in flight: [Qu (8) | Quu (8 x 8)]
+    static constexpr int SC_ZX = 288;  // x_k of the knot in flight (constraint rows read their slice from here)
+    static constexpr int SC_ZU = 296;  // u_k
+    static constexpr int SC_ITM = 304; // cost items [N (1 + ncon)]
 
-    ALTRO_HD double &W(int e) const { return ws[(size_t)e * stride]; }
-    ALTRO_HD double &sc(int i) const { return scr[i * ss]; }
-    ALTRO_HD double &mu(int c) const { return scr[(SC_MU + c) * ss]; }
+    ALTRO_HD double &W(int e) const { return lane_global(ws)[(size_t)e * stride]; }
+    ALTRO_HD double &sc(int i) const { return lane_shared(scr)[i * SS]; }
+    ALTRO_HD double &mu(int c) const { return lane_shared(scr)[(SC_MU + c) * SS]; }
+    ALTRO_HD void prefetch(int e) const { lane_prefetch(ws + (size_t)e * stride); }
 
-    ALTRO_HD Lane(const Params &P_, const LaneLayout &L_, double *ws_col, size_t stride_, double *scr_, int ss_, int inst_)
-        : P(P_), L(L_), ws(ws_col), stride(stride_), scr(scr_), ss(ss_), inst(inst_)
+    ALTRO_HD Lane(const Params &P_, const LaneConst<NX, NU> &C_, const LaneLayout &L_, double *ws_col, size_t stride_,
+                  double *scr_, const ConDesc *cd_, int inst_)
+        : P(P_), C(C_), L(L_), ws(ws_col), stride(stride_), scr(scr_), inst(inst_)
     {
         N = P.N;
         ncon = P.ncon;
-        cd = P.con;
+        cd = cd_;
         steps = P.steps > 0 ? P.steps : 1;
         st = 0;
         phase = LP_STEP_BEGIN;
@@ -135,10 +189,6 @@ struct Lane {
             sched = P.dyn_sched + (size_t)inst * P.sched_len + (a < b ? a : b);
         }
     }
-    ALTRO_HD size_t dyn_index(int k) const { return dyn_base + (sched ? (size_t)sched[k] : (size_t)dyn_k * k); }
-    ALTRO_HD const double *Ak(int k) const { return P.A + dyn_index(k) * n * n; }
-    ALTRO_HD const double *Bk(int k) const { return P.Bm + dyn_index(k) * n * m; }
-    ALTRO_HD const double *dk(int k) const { return P.d + dyn_index(k) * n; }
     ALTRO_HD size_t con_idx(const ConDesc &c, int k) const
     {
         if (c.track) {
@@ -210,47 +260,62 @@ struct Lane {
         }
     }
 
-    // ---------------------------------------------------------------- canonical sum (csum of the CTA kernel / oracle)
-    ALTRO_HD void vsum_begin() const
+    // ---------------------------------------------------------------- constraint values and costs (A.2, A.3)
+    // x_k and u_k of a trajectory into registers (one batch of independent loads) and into the scratch slice the
+    // constraint rows index at run time; the rows of the NEXT knot are prefetched into L1 meanwhile.
+    ALTRO_HD void stage_knot(int k, int oXc, int oUc, double (&x)[NX], double (&u)[NU], int knext) const
     {
-        for (int l = 0; l < 32; ++l) sc(SC_V + l) = 0.0;
-    }
-    ALTRO_HD void vsum_add(int it, double v) const { sc(SC_V + (it & 31)) += v; }
-    ALTRO_HD double vsum_end() const
-    {
-        for (int o = 16; o > 0; o >>= 1)
-            for (int l = 0; l < o; ++l) sc(SC_V + l) = sc(SC_V + l) + sc(SC_V + l + o);
-        return sc(SC_V);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = W(oXc + k * NX + i);
+        if (k < N - 1) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) u[i] = W(oUc + k * NU + i);
+        }
+        if (knext >= 0 && knext < N) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) prefetch(oXc + knext * NX + i);
+            if (knext < N - 1) {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) prefetch(oUc + knext * NU + i);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) sc(SC_ZX + i) = x[i];
+        if (k < N - 1) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) sc(SC_ZU + i) = u[i];
+        }
     }
 
-    // ---------------------------------------------------------------- constraint values and costs (A.2, A.3)
-    ALTRO_HD double row_value(const ConDesc &c, const double *G, const double *h, int zo, int r) const
+    // Row r of c = G z[inds] + h on the staged knot (TO.evaluate)
+    ALTRO_HD double row_value(const ConDesc &c, const double *G, const double *h, int zb, int r) const
     {
-        if (c.rowsparse) return fma(c.rs_coef[r], W(zo + c.inds[c.rs_col[r]]), h[r]);
+        if (c.rowsparse) return fma(lane_global(c.rs_coef)[r], sc(zb + c.inds[lane_global(c.rs_col)[r]]), h[r]);
         double acc = h[r];
         const double *g = G + r * c.w;
-        for (int j = 0; j < c.w; ++j) acc = fma(g[j], W(zo + c.inds[j]), acc);
+        for (int j = 0; j < c.w; ++j) acc = fma(g[j], sc(zb + c.inds[j]), acc);
         return acc;
     }
 
-    ALTRO_HD double con_cost(int ci, int k, int oXc, int oUc) const
+    // AL penalty term of block ci at the staged knot k
+    ALTRO_HD double con_cost(int ci, int k) const
     {
         const ConDesc &c = cd[ci];
         if (k < c.k0 || k >= c.k1) return 0.0;
         const size_t di = con_idx(c, k);
-        const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
-        const int zo = c.side == ALTRO_STATE ? oXc + k * n : oUc + k * m;
+        const double *G = lane_global(c.G) + di * c.p * c.w, *h = lane_global(c.h) + di * c.p;
+        const int zb = c.side == ALTRO_STATE ? SC_ZX : SC_ZU;
         const int lo = L.lam + c.dual_off + (k - c.k0) * c.p;
         const double mu_c = mu(ci);
         double Jc = 0.0;
         if (c.sense == ALTRO_EQUALITY) {
             for (int r = 0; r < c.p; ++r) {
-                const double v = row_value(c, G, h, zo, r);
+                const double v = row_value(c, G, h, zb, r);
                 Jc += W(lo + r) * v + 0.5 * mu_c * v * v;
             }
         } else if (c.sense == ALTRO_INEQUALITY) {
             for (int r = 0; r < c.p; ++r) {
-                const double v = row_value(c, G, h, zo, r), l = W(lo + r);
+                const double v = row_value(c, G, h, zb, r), l = W(lo + r);
                 const bool act = (v >= 0.0) || (l > 0.0);
                 Jc += l * v + (act ? 0.5 * mu_c * v * v : 0.0);
             }
@@ -258,7 +323,7 @@ struct Lane {
             double a2 = 0.0, t = 0.0, nl = 0.0;
             for (int r = 0; r < c.p; ++r) {
                 const double l = W(lo + r);
-                const double lb = l - mu_c * row_value(c, G, h, zo, r);
+                const double lb = l - mu_c * row_value(c, G, h, zb, r);
                 nl += l * l;
                 if (r < c.p - 1) a2 += lb * lb;
                 else t = lb;
@@ -273,52 +338,77 @@ struct Lane {
         return Jc;
     }
 
-    ALTRO_HD double stage_cost(int k, int oXc, int oUc) const
+    ALTRO_HD double stage_cost(int k, const double (&x)[NX], const double (&u)[NU]) const
     {
         double Jk = 0.0;
         if (k == N - 1) {
-            for (int i = 0; i < n; ++i) { const double e = W(oXc + k * n + i) - xref(k, i); Jk += 0.5 * P.Qf[i] * e * e; }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { const double e = x[i] - xref(k, i); Jk += 0.5 * C.Qf[i] * e * e; }
             return Jk;
         }
-        for (int i = 0; i < n; ++i) { const double e = W(oXc + k * n + i) - xref(k, i); Jk += 0.5 * P.Q[i] * e * e; }
-        for (int i = 0; i < m; ++i) { const double e = W(oUc + k * m + i) - uref(k, i); Jk += 0.5 * P.R[i] * e * e; }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { const double e = x[i] - xref(k, i); Jk += 0.5 * C.Q[i] * e * e; }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) { const double e = u[i] - uref(k, i); Jk += 0.5 * C.R[i] * e * e; }
         return Jk * P.dt;
     }
 
+    // Canonical sum of the cost items (csum of the CTA kernel / oracle): 32 strided partials, then a binary tree.
+    ALTRO_HD double item_sum(int count) const
+    {
+        for (int l = 0; l < 32; ++l) {
+            double a = 0.0;
+            for (int i = l; i < count; i += 32) a += sc(SC_ITM + i);
+            sc(SC_V + l) = a;
+        }
+        for (int o = 16; o > 0; o >>= 1)
+            for (int l = 0; l < o; ++l) sc(SC_V + l) = sc(SC_V + l) + sc(SC_V + l + o);
+        return sc(SC_V);
+    }
+
+    // AL cost of a trajectory: items it = piece * N + k (piece 0 = stage cost, 1 + ci = block ci), evaluated knot by
+    // knot (each knot is staged once) and summed in the canonical item order.
     ALTRO_HDN double al_cost(int oXc, int oUc) const
     {
-        vsum_begin();
-        int it = 0;
-        for (int k = 0; k < N; ++k, ++it) vsum_add(it, stage_cost(k, oXc, oUc));
-        for (int ci = 0; ci < ncon; ++ci)
-            for (int k = 0; k < N; ++k, ++it) vsum_add(it, con_cost(ci, k, oXc, oUc));
-        return vsum_end();
+        for (int k = 0; k < N; ++k) {
+            double x[NX], u[NU];
+            stage_knot(k, oXc, oUc, x, u, k + 1);
+            sc(SC_ITM + k) = stage_cost(k, x, u);
+            for (int ci = 0; ci < ncon; ++ci) sc(SC_ITM + (1 + ci) * N + k) = con_cost(ci, k);
+        }
+        return item_sum(N * (1 + ncon));
     }
 
     ALTRO_HD double objective_cost() const
     {
-        vsum_begin();
-        for (int k = 0; k < N; ++k) vsum_add(k, stage_cost(k, L.X, L.U));
-        return vsum_end();
+        for (int k = 0; k < N; ++k) {
+            double x[NX], u[NU];
+            stage_knot(k, L.X, L.U, x, u, k + 1);
+            sc(SC_ITM + k) = stage_cost(k, x, u);
+        }
+        return item_sum(N);
     }
 
     ALTRO_HDN double max_violation() const
     {
         double v = 0.0;
-        for (int ci = 0; ci < ncon; ++ci) {
-            const ConDesc &c = cd[ci];
-            for (int k = c.k0; k < c.k1; ++k) {
+        for (int k = 0; k < N; ++k) {
+            double x[NX], u[NU];
+            stage_knot(k, L.X, L.U, x, u, k + 1);
+            for (int ci = 0; ci < ncon; ++ci) {
+                const ConDesc &c = cd[ci];
+                if (k < c.k0 || k >= c.k1) continue;
                 const size_t di = con_idx(c, k);
-                const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
-                const int zo = c.side == ALTRO_STATE ? L.X + k * n : L.U + k * m;
+                const double *G = lane_global(c.G) + di * c.p * c.w, *h = lane_global(c.h) + di * c.p;
+                const int zb = c.side == ALTRO_STATE ? SC_ZX : SC_ZU;
                 if (c.sense == ALTRO_EQUALITY) {
-                    for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, zo, r)));
+                    for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, zb, r)));
                 } else if (c.sense == ALTRO_INEQUALITY) {
-                    for (int r = 0; r < c.p; ++r) v = fmax(v, row_value(c, G, h, zo, r));
+                    for (int r = 0; r < c.p; ++r) v = fmax(v, row_value(c, G, h, zb, r));
                 } else {
                     double a2 = 0.0, t = 0.0;
                     for (int r = 0; r < c.p; ++r) {
-                        const double cv = row_value(c, G, h, zo, r);
+                        const double cv = row_value(c, G, h, zb, r);
                         if (r < c.p - 1) a2 += cv * cv;
                         else t = cv;
                     }
@@ -326,10 +416,10 @@ struct Lane {
                     if (!P.o.soc_viol_proj) {
                         v = fmax(v, a - t);
                     } else if (a <= -t) {
-                        for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, zo, r)));
+                        for (int r = 0; r < c.p; ++r) v = fmax(v, fabs(row_value(c, G, h, zb, r)));
                     } else if (a > t) {
                         const double cf = 0.5 * (1.0 + t / a);
-                        for (int r = 0; r < c.p - 1; ++r) v = fmax(v, fabs((1.0 - cf) * row_value(c, G, h, zo, r)));
+                        for (int r = 0; r < c.p - 1; ++r) v = fmax(v, fabs((1.0 - cf) * row_value(c, G, h, zb, r)));
                         v = fmax(v, fabs(t - cf * a));
                     }
                 }
@@ -340,24 +430,27 @@ struct Lane {
 
     ALTRO_HDN void dual_update() const
     {
-        for (int ci = 0; ci < ncon; ++ci) {
-            const ConDesc &c = cd[ci];
-            const double mu_c = mu(ci);
-            for (int k = c.k0; k < c.k1; ++k) {
+        for (int k = 0; k < N; ++k) {
+            double x[NX], u[NU];
+            stage_knot(k, L.X, L.U, x, u, k + 1);
+            for (int ci = 0; ci < ncon; ++ci) {
+                const ConDesc &c = cd[ci];
+                if (k < c.k0 || k >= c.k1) continue;
+                const double mu_c = mu(ci);
                 const size_t di = con_idx(c, k);
-                const double *G = c.G + di * c.p * c.w, *h = c.h + di * c.p;
-                const int zo = c.side == ALTRO_STATE ? L.X + k * n : L.U + k * m;
+                const double *G = lane_global(c.G) + di * c.p * c.w, *h = lane_global(c.h) + di * c.p;
+                const int zb = c.side == ALTRO_STATE ? SC_ZX : SC_ZU;
                 const int lo = L.lam + c.dual_off + (k - c.k0) * c.p;
                 if (c.sense == ALTRO_EQUALITY) {
                     for (int r = 0; r < c.p; ++r)
-                        W(lo + r) = fmin(fmax(W(lo + r) + mu_c * row_value(c, G, h, zo, r), -P.o.dual_max), P.o.dual_max);
+                        W(lo + r) = fmin(fmax(W(lo + r) + mu_c * row_value(c, G, h, zb, r), -P.o.dual_max), P.o.dual_max);
                 } else if (c.sense == ALTRO_INEQUALITY) {
                     for (int r = 0; r < c.p; ++r)
-                        W(lo + r) = fmin(fmax(W(lo + r) + mu_c * row_value(c, G, h, zo, r), 0.0), P.o.dual_max);
+                        W(lo + r) = fmin(fmax(W(lo + r) + mu_c * row_value(c, G, h, zb, r), 0.0), P.o.dual_max);
                 } else {
                     double a2 = 0.0, t = 0.0;
                     for (int r = 0; r < c.p; ++r) {
-                        const double lb = W(lo + r) - mu_c * row_value(c, G, h, zo, r);
+                        const double lb = W(lo + r) - mu_c * row_value(c, G, h, zb, r);
                         W(lo + r) = lb;
                         if (r < c.p - 1) a2 += lb * lb;
                         else t = lb;
@@ -376,28 +469,28 @@ struct Lane {
     }
 
     // ---------------------------------------------------------------- AL expansion of one (block, knot) (A.3)
-    // g[w] and H (w x w dense symmetric, or w diagonal entries for row-sparse blocks) into the scratch at SC_G.
+    // g[w] and H (w x w dense symmetric, or w diagonal entries for row-sparse blocks) of the staged knot into SC_G.
     ALTRO_HD void expand_block(const ConDesc &c, int ci, int k) const
     {
         const double mu_c = mu(ci);
         const int w = c.w, p = c.p;
         const size_t di = con_idx(c, k);
-        const double *G = c.G + di * p * w, *h = c.h + di * p;
-        const int zo = c.side == ALTRO_STATE ? L.X + k * n : L.U + k * m;
+        const double *G = lane_global(c.G) + di * p * w, *h = lane_global(c.h) + di * p;
+        const int zb = c.side == ALTRO_STATE ? SC_ZX : SC_ZU;
         const int lo = L.lam + c.dual_off + (k - c.k0) * p;
         const int g = SC_G, H = SC_G + w;
         if (c.rowsparse) {
             for (int j = 0; j < 2 * w; ++j) sc(g + j) = 0.0;
             for (int r = 0; r < p; ++r) {
-                const double v = row_value(c, G, h, zo, r), cf = c.rs_coef[r], l = W(lo + r);
+                const double v = row_value(c, G, h, zb, r), cf = lane_global(c.rs_coef)[r], l = W(lo + r);
                 const bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l > 0.0);
-                const int col = c.rs_col[r];
+                const int col = lane_global(c.rs_col)[r];
                 sc(g + col) += cf * (l + (act ? mu_c * v : 0.0));
                 sc(H + col) += act ? cf * cf * mu_c : 0.0;
             }
         } else if (c.sense != ALTRO_SECOND_ORDER_CONE) {
             for (int r = 0; r < p; ++r) {
-                const double v = row_value(c, G, h, zo, r), l = W(lo + r);
+                const double v = row_value(c, G, h, zb, r), l = W(lo + r);
                 const bool act = c.sense == ALTRO_EQUALITY || (v >= 0.0) || (l > 0.0);
                 sc(SC_Y + r) = l + (act ? mu_c * v : 0.0);
                 sc(SC_D + r) = act ? mu_c : 0.0;
@@ -417,7 +510,7 @@ struct Lane {
         } else {
             double a2 = 0.0;
             for (int r = 0; r < p; ++r) {
-                const double lb = W(lo + r) - mu_c * row_value(c, G, h, zo, r);
+                const double lb = W(lo + r) - mu_c * row_value(c, G, h, zb, r);
                 sc(SC_Y + r) = lb;
                 if (r < p - 1) a2 += lb * lb;
             }
@@ -460,9 +553,10 @@ struct Lane {
         }
     }
 
-    // Adds the expansions of every block of `side` active at knot k to the vector and the LD x LD matrix that the caller
-    // initialised at scratch offset `at` ([vec (8) | mat]), in ascending block order (the oracle's scatter_expansion).
-    // The targets are run-time indices, hence scratch; the backward pass reads them back with compile-time offsets.
+    // Adds the expansions of every block of `side` active at the staged knot k to the vector and the LD x LD matrix
+    // that the caller initialised at scratch offset `at` ([vec (8) | mat]), in ascending block order (the oracle's
+    // scatter_expansion).  The targets are run-time indices, hence scratch; the backward pass reads them back with
+    // compile-time offsets.
     ALTRO_HD void add_expansions(int k, int side, int at, int LD) const
     {
         for (int ci = 0; ci < ncon; ++ci) {
@@ -481,6 +575,17 @@ struct Lane {
                 for (int i = 0; i < w; ++i)
                     for (int j = 0; j < w; ++j) sc(at + 8 + c.inds[i] * LD + c.inds[j]) += sc(SC_G + w + i * w + j);
             }
+        }
+    }
+
+    // prefetch the duals of every block at knot k (the expansion of that knot reads them next)
+    ALTRO_HD void prefetch_duals(int k) const
+    {
+        for (int ci = 0; ci < ncon; ++ci) {
+            const ConDesc &c = cd[ci];
+            if (k < c.k0 || k >= c.k1) continue;
+            const int lo = L.lam + c.dual_off + (k - c.k0) * c.p;
+            for (int r = 0; r < c.p; ++r) prefetch(lo + r);
         }
     }
 
@@ -505,22 +610,30 @@ struct Lane {
             double a1 = 0.0, a2 = 0.0;
             double S[NX * NX], s[NX];
             // terminal cost-to-go
+            {
+                double x[NX], u[NU];
+                prefetch_duals(N - 1);
+                stage_knot(N - 1, L.X, L.U, x, u, N - 2);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
+                for (int i = 0; i < NX; ++i) {
 #pragma unroll
-                for (int j = 0; j < NX; ++j) sc(SC_EX + 8 + i * NX + j) = (i == j) ? P.Qf[i] : 0.0;
-                sc(SC_EX + i) = P.Qf[i] * (W(L.X + (N - 1) * NX + i) - xref(N - 1, i));
-            }
-            add_expansions(N - 1, ALTRO_STATE, SC_EX, NX);
+                    for (int j = 0; j < NX; ++j) sc(SC_EX + 8 + i * NX + j) = (i == j) ? C.Qf[i] : 0.0;
+                    sc(SC_EX + i) = C.Qf[i] * (x[i] - xref(N - 1, i));
+                }
+                add_expansions(N - 1, ALTRO_STATE, SC_EX, NX);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
+                for (int i = 0; i < NX; ++i) {
 #pragma unroll
-                for (int j = 0; j < NX; ++j) S[i * NX + j] = sc(SC_EX + 8 + i * NX + j);
-                s[i] = sc(SC_EX + i);
+                    for (int j = 0; j < NX; ++j) S[i * NX + j] = sc(SC_EX + 8 + i * NX + j);
+                    s[i] = sc(SC_EX + i);
+                }
             }
             bool bad = false;
             for (int k = N - 2; k >= 0; --k) {
-                const double *A = Ak(k), *Bm = Bk(k);
+                // this knot's state / control / duals: staged first, the previous knot's rows prefetched
+                double xk[NX], uk[NU];
+                prefetch_duals(k);
+                stage_knot(k, L.X, L.U, xk, uk, k - 1);
                 double SA[NX * NX], SB[NX * NU];
 #pragma unroll
                 for (int i = 0; i < NX; ++i) {
@@ -528,14 +641,14 @@ struct Lane {
                     for (int j = 0; j < NX; ++j) {
                         double acc = 0.0;
 #pragma unroll
-                        for (int l = 0; l < NX; ++l) acc = fma(S[i * NX + l], A[l * NX + j], acc);
+                        for (int l = 0; l < NX; ++l) acc = fma(S[i * NX + l], C.A[l * NX + j], acc);
                         SA[i * NX + j] = acc;
                     }
 #pragma unroll
                     for (int j = 0; j < NU; ++j) {
                         double acc = 0.0;
 #pragma unroll
-                        for (int l = 0; l < NX; ++l) acc = fma(S[i * NX + l], Bm[l * NU + j], acc);
+                        for (int l = 0; l < NX; ++l) acc = fma(S[i * NX + l], C.B[l * NU + j], acc);
                         SB[i * NU + j] = acc;
                     }
                 }
@@ -544,14 +657,14 @@ struct Lane {
 #pragma unroll
                 for (int i = 0; i < NX; ++i) {
 #pragma unroll
-                    for (int j = 0; j < NX; ++j) sc(SC_EX + 8 + i * NX + j) = (i == j) ? dt * P.Q[i] : 0.0;
-                    sc(SC_EX + i) = dt * P.Q[i] * (W(L.X + k * NX + i) - xref(k, i));
+                    for (int j = 0; j < NX; ++j) sc(SC_EX + 8 + i * NX + j) = (i == j) ? dt * C.Q[i] : 0.0;
+                    sc(SC_EX + i) = dt * C.Q[i] * (xk[i] - xref(k, i));
                 }
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
 #pragma unroll
-                    for (int j = 0; j < NU; ++j) sc(SC_EU + 8 + i * NU + j) = (i == j) ? dt * P.R[i] : 0.0;
-                    sc(SC_EU + i) = dt * P.R[i] * (W(L.U + k * NU + i) - uref(k, i));
+                    for (int j = 0; j < NU; ++j) sc(SC_EU + 8 + i * NU + j) = (i == j) ? dt * C.R[i] : 0.0;
+                    sc(SC_EU + i) = dt * C.R[i] * (uk[i] - uref(k, i));
                 }
                 add_expansions(k, ALTRO_STATE, SC_EX, NX);
                 add_expansions(k, ALTRO_CONTROL, SC_EU, NU);
@@ -575,7 +688,7 @@ struct Lane {
                     for (int j = 0; j < NX; ++j) {
                         double acc = Qxx[i * NX + j];
 #pragma unroll
-                        for (int l = 0; l < NX; ++l) acc = fma(A[l * NX + i], SA[l * NX + j], acc);
+                        for (int l = 0; l < NX; ++l) acc = fma(C.A[l * NX + i], SA[l * NX + j], acc);
                         Qxx[i * NX + j] = acc;
                     }
 #pragma unroll
@@ -584,7 +697,7 @@ struct Lane {
                     for (int j = 0; j < NX; ++j) {
                         double acc = 0.0;
 #pragma unroll
-                        for (int l = 0; l < NX; ++l) acc = fma(Bm[l * NU + i], SA[l * NX + j], acc);
+                        for (int l = 0; l < NX; ++l) acc = fma(C.B[l * NU + i], SA[l * NX + j], acc);
                         Qux[i * NX + j] = acc;
                     }
 #pragma unroll
@@ -593,21 +706,21 @@ struct Lane {
                     for (int j = 0; j < NU; ++j) {
                         double acc = Quu[i * NU + j];
 #pragma unroll
-                        for (int l = 0; l < NX; ++l) acc = fma(Bm[l * NU + i], SB[l * NU + j], acc);
+                        for (int l = 0; l < NX; ++l) acc = fma(C.B[l * NU + i], SB[l * NU + j], acc);
                         Quu[i * NU + j] = acc;
                     }
 #pragma unroll
                 for (int i = 0; i < NX; ++i) {
                     double acc = Qx[i];
 #pragma unroll
-                    for (int l = 0; l < NX; ++l) acc = fma(A[l * NX + i], s[l], acc);
+                    for (int l = 0; l < NX; ++l) acc = fma(C.A[l * NX + i], s[l], acc);
                     Qx[i] = acc;
                 }
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
                     double acc = Qu[i];
 #pragma unroll
-                    for (int l = 0; l < NX; ++l) acc = fma(Bm[l * NU + i], s[l], acc);
+                    for (int l = 0; l < NX; ++l) acc = fma(C.B[l * NU + i], s[l], acc);
                     Qu[i] = acc;
                 }
                 // LDL' of Quu + rho I: un-normalised lower factor, reciprocal pivots
@@ -725,22 +838,29 @@ struct Lane {
     // ---------------------------------------------------------------- rollouts (A.6, A.8)
     ALTRO_HDN void rollout_open_loop() const
     {
-        for (int k = 0; k < N - 1; ++k) {
-            const double *A = Ak(k), *Bm = Bk(k), *d = dk(k);
-            double x[NX], u[NU];
+        double x[NX];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) x[j] = W(L.X + k * NX + j);
+        for (int j = 0; j < NX; ++j) x[j] = W(L.X + j);
+        for (int k = 0; k < N - 1; ++k) {
+            double u[NU], xn[NX];
 #pragma unroll
             for (int j = 0; j < NU; ++j) u[j] = W(L.U + k * NU + j);
+            if (k + 1 < N - 1) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) prefetch(L.U + (k + 1) * NU + j);
+            }
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
-                double acc = d[i];
+                double acc = C.d[i];
 #pragma unroll
-                for (int j = 0; j < NX; ++j) acc = fma(A[i * NX + j], x[j], acc);
+                for (int j = 0; j < NX; ++j) acc = fma(C.A[i * NX + j], x[j], acc);
 #pragma unroll
-                for (int j = 0; j < NU; ++j) acc = fma(Bm[i * NU + j], u[j], acc);
+                for (int j = 0; j < NU; ++j) acc = fma(C.B[i * NU + j], u[j], acc);
+                xn[i] = acc;
                 W(L.X + (k + 1) * NX + i) = acc;
             }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = xn[i];
         }
     }
 
@@ -752,32 +872,46 @@ struct Lane {
 #pragma unroll
         for (int i = 0; i < NX; ++i) { xb[i] = W(L.X + i); W(L.Xb + i) = xb[i]; }
         for (int k = 0; k < N - 1; ++k) {
-            const double *A = Ak(k), *Bm = Bk(k), *d = dk(k);
+            // one batch of independent loads for this knot, the next knot's rows prefetched
+            double xo[NX], xo1[NX], uo[NU], dvo[NU], Kk[NU * NX];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) { xo[j] = W(L.X + k * NX + j); xo1[j] = W(L.X + (k + 1) * NX + j); }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) { uo[i] = W(L.U + k * NU + i); dvo[i] = W(L.dv + k * NU + i); }
+#pragma unroll
+            for (int i = 0; i < NU * NX; ++i) Kk[i] = W(L.K + k * NU * NX + i);
+            if (k + 1 < N - 1) {
+#pragma unroll
+                for (int i = 0; i < NU * NX; ++i) prefetch(L.K + (k + 1) * NU * NX + i);
+#pragma unroll
+                for (int i = 0; i < NU; ++i) { prefetch(L.U + (k + 1) * NU + i); prefetch(L.dv + (k + 1) * NU + i); }
+#pragma unroll
+                for (int j = 0; j < NX; ++j) prefetch(L.X + (k + 2) * NX + j);
+            }
             double dx[NX], ub[NU];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) dx[j] = xb[j] - W(L.X + k * NX + j);
+            for (int j = 0; j < NX; ++j) dx[j] = xb[j] - xo[j];
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
-                const double u = W(L.U + k * NU + i);
-                double acc = fma(al, W(L.dv + k * NU + i), u);
+                double acc = fma(al, dvo[i], uo[i]);
 #pragma unroll
-                for (int j = 0; j < NX; ++j) acc = fma(W(L.K + k * NU * NX + i * NX + j), dx[j], acc);
+                for (int j = 0; j < NX; ++j) acc = fma(Kk[i * NX + j], dx[j], acc);
                 ub[i] = acc;
                 W(L.Ub + k * NU + i) = acc;
-                if (!(acc == u)) same = false;
+                if (!(acc == uo[i])) same = false;
             }
             double xn[NX];
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
-                double acc = d[i];
+                double acc = C.d[i];
 #pragma unroll
-                for (int j = 0; j < NX; ++j) acc = fma(A[i * NX + j], xb[j], acc);
+                for (int j = 0; j < NX; ++j) acc = fma(C.A[i * NX + j], xb[j], acc);
 #pragma unroll
-                for (int j = 0; j < NU; ++j) acc = fma(Bm[i * NU + j], ub[j], acc);
+                for (int j = 0; j < NU; ++j) acc = fma(C.B[i * NU + j], ub[j], acc);
                 xn[i] = acc;
                 W(L.Xb + (k + 1) * NX + i) = acc;
                 if (!(fabs(acc) <= P.o.max_state_value)) bad = true;
-                else if (!(acc == W(L.X + (k + 1) * NX + i))) same = false;
+                else if (!(acc == xo1[i])) same = false;
             }
 #pragma unroll
             for (int i = 0; i < NX; ++i) xb[i] = xn[i];
@@ -787,25 +921,27 @@ struct Lane {
 
     ALTRO_HD void copy_traj(int oXd, int oUd, int oXs, int oUs) const
     {
+#pragma unroll 6
         for (int i = 0; i < N * n; ++i) W(oXd + i) = W(oXs + i);
+#pragma unroll 6
         for (int i = 0; i < (N - 1) * m; ++i) W(oUd + i) = W(oUs + i);
     }
 
     ALTRO_HD double gradient_todorov() const
     {
-        vsum_begin();
         for (int k = 0; k < N - 1; ++k) {
             double mx = 0.0;
-            for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(W(L.dv + k * m + i)) / (fabs(W(L.U + k * m + i)) + 1.0));
-            vsum_add(k, mx);
+#pragma unroll
+            for (int i = 0; i < NU; ++i) mx = fmax(mx, fabs(W(L.dv + k * NU + i)) / (fabs(W(L.U + k * NU + i)) + 1.0));
+            sc(SC_ITM + k) = mx;
         }
-        return vsum_end() / (double)(N - 1);
+        return item_sum(N - 1) / (double)(N - 1);
     }
 
     // ---------------------------------------------------------------- warm-started MPC transition
     ALTRO_HDN void transition(int s)
     {
-        const double *zz = P.noise ? P.noise + ((size_t)s * P.B + inst) * n : nullptr;
+        const double *zz = P.noise ? lane_global(P.noise) + ((size_t)s * P.B + inst) * n : nullptr;
         double s0 = P.noise_w1, s1 = P.noise_w1;
         if (zz) {
             if (P.noise_mode == 1) {
@@ -826,9 +962,11 @@ struct Lane {
             W(L.X + i) = v;
         }
         if (P.shift) {
+#pragma unroll 6
             for (int i = 0; i < (N - 2) * m; ++i) W(L.U + i) = W(L.U + i + m);
             for (int ci = 0; ci < ncon; ++ci) {
                 const int cnt = (cd[ci].k1 - cd[ci].k0 - 1) * cd[ci].p, p = cd[ci].p, lo = L.lam + cd[ci].dual_off;
+#pragma unroll 4
                 for (int i = 0; i < cnt; ++i) W(lo + i) = W(lo + i + p);
             }
         }
@@ -983,17 +1121,30 @@ struct Lane {
 
 #ifdef __CUDACC__
 
-// One warp = 32 instances; CTAs of WPC warps (no communication between warps).
-template <int NX, int NU, int WPC>
-__global__ void __launch_bounds__(32 * WPC) altro_lane_kernel(const __grid_constant__ Params P, const LaneLayout L,
-                                                              double *ws, size_t stride)
+// One warp advances LPW instances (lanes 0 .. LPW-1; the other lanes idle): with a few thousand instances per GPU,
+// fewer instances per warp means more warps, i.e. more of the 4 x 148 schedulers busy and more latency hidden, at
+// the price of issuing each instruction for fewer instances.  One CTA = one warp; no communication between warps.
+template <int NX, int NU, int LPW>
+__global__ void __launch_bounds__(32) altro_lane_kernel(const __grid_constant__ Params P,
+                                                        const __grid_constant__ LaneConst<NX, NU> C, const LaneLayout L,
+                                                        double *ws, size_t stride, int scratch_per_lane)
 {
-    extern __shared__ __align__(16) double lane_scratch[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int inst = (blockIdx.x * WPC + warp) * 32 + lane;
-    const bool valid = inst < P.B;
-    double *scr = lane_scratch + (size_t)warp * LANE_SCRATCH * 32 + lane;
-    Lane<NX, NU> ln(P, L, ws + (valid ? inst : 0), stride, scr, 32, valid ? inst + P.inst_offset : P.inst_offset);
+    extern __shared__ __align__(16) double lane_smem[];
+    const int lane = threadIdx.x;
+    // descriptors first (shared by the warp's lanes), the per-lane scratch behind them
+    ConDesc *cds = reinterpret_cast<ConDesc *>(lane_smem);
+    {
+        const int words = P.ncon * (int)(sizeof(ConDesc) / sizeof(int));
+        const int *src = reinterpret_cast<const int *>(P.con);
+        int *dst = reinterpret_cast<int *>(cds);
+        for (int i = lane; i < words; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    double *scr = lane_smem + (size_t)(P.ncon > 0 ? P.ncon : 1) * (sizeof(ConDesc) / sizeof(double)) + lane;
+    (void)scratch_per_lane;
+    const int inst = blockIdx.x * LPW + lane;
+    const bool valid = lane < LPW && inst < P.B;
+    Lane<NX, NU, LPW> ln(P, C, L, ws + (valid ? inst : 0), stride, scr, cds, valid ? inst + P.inst_offset : P.inst_offset);
     if (!valid) ln.phase = LP_DONE;
     else ln.load();
     while (__any_sync(0xffffffffu, ln.phase != LP_DONE)) {

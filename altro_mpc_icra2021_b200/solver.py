@@ -26,7 +26,7 @@ import numpy as np
 from .problem import Problem, SolverOptions, STATUS_NAMES, SOLVE_SUCCEEDED
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaltro_b200.so")
+LIB_PATH = os.environ.get("ALTRO_B200_LIB") or os.path.join(_HERE, "libaltro_b200.so")  # (env override: development builds)
 
 ABI_SYMBOLS = [
     "altro_default_options", "altro_create", "altro_destroy", "altro_last_error", "altro_set_stream",
@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "altro_get_run_results",
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
     "altro_set_line_search_mode", "altro_get_line_search_mode", "altro_reserve_steps",
-    "altro_set_kernel_mode", "altro_get_kernel_mode",
+    "altro_set_kernel_mode", "altro_get_kernel_mode", "altro_set_run_queue",
     "altro_measure_peaks",
 ]
 
@@ -382,6 +382,11 @@ class ALTROSolver:
         self._ck(self.lib.altro_get_phase_cycles(self.h, int(enable), _p(out)))
         return out
 
+    def set_run_queue(self, steps_per_item: int) -> None:
+        """Scheduling of mpc_run: >= 1 = persistent grid + work queue of (instance, steps_per_item steps) items
+        (default 1), 0 = one CTA per instance for the whole run."""
+        self._ck(self.lib.altro_set_run_queue(self.h, int(steps_per_item)))
+
     def reserve_steps(self, steps: int):
         """Pre-sizes the per-step statistics / log buffers (otherwise the first longer mpc_run reallocates them)."""
         self.upload()
@@ -396,11 +401,11 @@ class ALTROSolver:
         spec = C.c_int()
         self._ck(self.lib.altro_get_line_search_mode(self.h, C.byref(spec)))
         info["speculative_line_search"] = bool(spec.value)
-        km, lr, lsm = C.c_int(), C.c_int(), C.c_int()
-        self._ck(self.lib.altro_get_kernel_mode(self.h, C.byref(km), C.byref(lr), C.byref(lsm)))
+        km, lr, lsm, lpw = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.altro_get_kernel_mode(self.h, C.byref(km), C.byref(lr), C.byref(lsm), C.byref(lpw)))
         info["kernel"] = "lane" if km.value == 2 else "cta"
         if km.value == 2:
-            info.update(lane_regs_per_thread=lr.value, lane_smem_bytes=lsm.value, instances_per_warp=32)
+            info.update(lane_regs_per_thread=lr.value, lane_smem_bytes=lsm.value, instances_per_warp=lpw.value)
         return info
 
     def all_succeeded(self) -> bool:

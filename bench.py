@@ -6,16 +6,25 @@ One *step* = one pass of the hot path over one batch: the warm-started MPC trans
 the batched AL-iLQR solve!  -- the body of the reference's MPC loops (random_linear_problem.jl:121-161,
 simple_rocket.jl:59-82,163-174, altro_solver.jl:44-72).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rocket|quadruped|quadruped_soc|random_linear|flexsat]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rocket|quadruped|quadruped_soc|random_linear|grasp|flexsat]
   torchrun ... bench.py --gpus N ...      one rank per GPU, 4096 instances per GPU (weak scaling), no collective on
                                           the solve path; NCCL only gathers the per-instance statistics at the end
   python bench.py --impl reference ...    the reference arm: the CPU oracle (a port -- Julia Altro.jl cannot run here)
-                                          with all host threads on the same workload
+                                          with all host threads on the same workloads
 
-`value`  : whole-job solves/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks.
-`e2e`    : same metric through the public API with HOST buffers (pinned H2D of x0 + reference, D2H of X, U, stats).
-`roofline`: FP64 (DFMA) roofline of the solve kernel -- algorithmic flops from the per-instance iteration and
-           line-search counts (SURVEY.md 8d formulas) / CUDA-event duration / DFMA peak measured in this run.
+The headline keys describe configs[1] of BASELINE.json (rocket, 4096 instances per GPU); `workloads` carries the same
+measurements for configs[2] (quadruped, 4096 instances per GPU) so that the 1/2/4/8-GPU scaling runs record both
+families the target names.  --workload X makes X the headline and drops the secondary workloads.
+
+`value`        : whole-job solves/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+                 (closed-loop run: K x {transition; solve!} per instance in one launch).
+`e2e`          : the same run through the public API with HOST buffers (pinned H2D of the disturbances, D2H of the
+                 closed-loop states, controls, statistics, X, U inside the timed region).
+`per_step_api` : the reference-shaped usage, one solve! call per MPC step: `value` with device-resident inputs (one
+                 transition + one solve launch per step), `e2e` with x0 and the reference window uploaded from host
+                 buffers and X, U and the statistics read back EVERY step.
+`roofline`     : FP64 (DFMA) roofline of the solve kernel -- algorithmic flops from the per-instance iteration and
+                 line-search counts (SURVEY.md 8d formulas) / CUDA-event duration / DFMA peak measured in this run.
 """
 from __future__ import annotations
 
@@ -33,6 +42,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from altro_mpc_icra2021_b200.problem import STATUS_NAMES  # noqa: E402
 from altro_mpc_icra2021_b200.problems import flexsat, grasp, mpc, quadruped, random_linear, rocket  # noqa: E402
 
 METRIC = "batched MPC solves/sec (whole box, device-timed)"
@@ -51,7 +61,6 @@ class Workload:
         self.track = None
         self.noise_model = (0, 0.0, 0.0)
         self.shift = True
-        self.qstate = None
         if name == "rocket":
             # configs[1]: 4096 instances, three second-order cones, warm-started shift MPC, N = 21
             cold = rocket.cold_problem()
@@ -107,21 +116,6 @@ class Workload:
         sp = np.linalg.norm(x[..., :h], axis=-1, keepdims=True) * w1
         sv = np.linalg.norm(x[..., h:], axis=-1, keepdims=True) * w2
         return x + z * np.concatenate([np.broadcast_to(sp, x[..., :h].shape), np.broadcast_to(sv, x[..., h:].shape)], -1)
-
-    def host_advance(self, prob, solver, z):
-        """The reference's between-solve update done by the caller on HOST buffers (e2e and CPU arms)."""
-        prob.kidx += 1
-        if self.qstate is not None:  # quadruped control tick: new contact schedule -> new B_k, plant step + noise
-            quadruped.advance(prob, self.qstate, self.rng)
-            solver.shift_fill(True, True)
-            return
-        x0 = self.apply_noise(prob.X[:, 1, :], z)  # x_1 of the last solution = plant step with its first control
-        prob.set_initial_state(x0)
-        if self.track is not None:
-            self.k = self.k + 1
-            prob.update_trajectory(*mpc.window_reference(self.track[0], self.track[1], self.k, prob.N))
-        if self.shift:
-            solver.shift_fill(True, True)
 
 
 def flops_model(prob, iters, outer, trials):
@@ -228,22 +222,6 @@ def oracle_arm(wl: Workload, steps, warmup, nthreads):
     prob = copy.deepcopy(wl.prob)
     op = OracleProblem(prob)
     op.solve(wl.opts, nthreads=nthreads)  # initial solve (random_linear_problem.jl:113), not timed
-    if wl.qstate is not None:  # quadruped: the contact schedule is rebuilt on the host every tick (lock-step)
-        class _S:
-            def shift_fill(self, primal=True, dual=True):
-                op.shift_fill(primal, dual)
-
-        total, iters, status = 0.0, [], []
-        for st in range(steps + warmup):
-            wl.host_advance(prob, _S(), None)
-            t0 = time.perf_counter()
-            r = op.solve(wl.opts, nthreads=nthreads)
-            if st >= warmup:
-                total += time.perf_counter() - t0
-                iters.append(r.iterations.mean())
-                status.append(np.mean(r.status == 1))
-        return {"value": prob.B * steps / total, "seconds": total, "iters_mean": float(np.mean(iters)),
-                "success": float(np.mean(status))}
     k = wl.k.copy()
     if warmup:
         op.mpc_run(wl.opts, warmup, wl.noise_samples(warmup), wl.noise_model, wl.track, k, wl.shift, nthreads)
@@ -256,6 +234,222 @@ def oracle_arm(wl: Workload, steps, warmup, nthreads):
             "success": float(np.mean(r["status"] == 1))}
 
 
+# ----------------------------------------------------------------------------- one workload on the GPU
+
+
+def bench_gpu_workload(name, args, K, W, rank, world, local, stream, dev, flush, peaks, make_solver, barrier, S, sharding):
+    """All GPU measurements of one workload; returns the dict that becomes the headline line or a `workloads` entry."""
+    import torch
+
+    seed = 0xA1720 + 2 + 1000 * rank
+    wl = Workload(name, args.batch, seed, make_solver)
+    prob, B = wl.prob, wl.batch
+    sv = make_solver(prob, wl.opts, threads_per_instance=args.threads_per_instance, pin=True)
+    if wl.track is not None:
+        sv.set_track(wl.track[0], wl.track[1], wl.k)  # before the first launch: the window is then read from the track
+    info = sv.launch_info()
+    sv.set_noise_model(*wl.noise_model)
+    zs_all = wl.noise_samples(max(W, 1) + K)
+    sv.set_noise_bank(zs_all)
+
+    # ---- initial solve + warm-up (untimed)
+    sv.solve()
+    init_ok = float(np.mean(sv.stats.status == 1))
+    if W:
+        sv.mpc_run(W, shift=wl.shift)
+    sv.reserve_steps(K)  # log buffers sized before the timed region (no cudaFree/cudaMalloc inside it)
+    sv.snapshot()  # the per-step and e2e phases replay the same K steps from this state
+    k_snap = wl.k.copy() + W
+    barrier()
+    # ---- timed region: K steps in one closed-loop launch, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    flush.zero_()  # L2 flush before the timed launch (256 MB write, outside the event pair)
+    e0.record(stream)
+    sv.mpc_run(K, shift=wl.shift, fetch=False)
+    e1.record(stream)
+    rr = sv.run_results(K)  # D2H after the event pair: needed for the flop model, not timed
+    barrier()
+    wall = time.perf_counter() - t_wall
+    sampler.stop_flag.set()
+    sampler.join()
+    kern_s = rr["device_ms"] * 1e-3
+    step_s = e0.elapsed_time(e1) * 1e-3
+    total_s = sharding.max_over_ranks(step_s)
+    flops = flops_model(prob, rr["iterations"], rr["iterations_outer"], rr["ls_trials"])
+    status_counts = {STATUS_NAMES[int(k)]: int(v) for k, v in zip(*np.unique(rr["status"], return_counts=True))}
+    gathered = sharding.gather_stats({"iterations": rr["iterations"][-1], "status": rr["status"][-1]})
+
+    # ---- per-step API, device-resident inputs: one transition + one solve launch per MPC step
+    sv.restore()
+    evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for st in range(K):
+        flush.zero_()
+        evl[st][0].record(stream)
+        sv.mpc_transition(None, shift=wl.shift)
+        sv.solve(fetch=False)
+        evl[st][1].record(stream)
+    barrier()
+    t_lock = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evl) * 1e-3)
+    sv.fetch()
+    per_step = {"value": B * world * K / t_lock, "unit": UNIT, "ms_per_step": 1e3 * t_lock / K,
+                "note": "one altro_mpc_transition + one altro_solve launch per MPC step (solve! once per step, as the "
+                        "reference's loops do); every step waits for its slowest instance"}
+
+    e2e = None
+    if not args.no_e2e:
+        # ---- e2e of the closed-loop run: pinned H2D of the K x B x n disturbances, the run, D2H of everything
+        barrier()
+        sv.restore()
+        zs = np.ascontiguousarray(zs_all[W:W + K])  # the same disturbances the device-timed run consumed
+        sv.lib.altro_host_register(S._p(zs), zs.nbytes)
+        h2d = zs.nbytes / K
+        d2h = (K * B * (prob.n + prob.m) * 8 + K * B * (4 * 4 + 2 * 8 + 8) + prob.X.nbytes + prob.U.nbytes) / K
+        t0 = time.perf_counter()
+        sv.set_noise_bank(zs)  # H2D of this run's inputs
+        sv.mpc_run(K, shift=wl.shift, fetch=True)  # run + D2H of closed-loop states, controls, statistics, X, U
+        t_e2e = time.perf_counter() - t0
+        sv.lib.altro_host_unregister(S._p(zs))
+        barrier()
+        t_e2e = sharding.max_over_ranks(t_e2e)
+        e2e = {"value": B * world * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / K}
+        # ---- e2e of the per-step API: every step the caller uploads its inputs from host buffers and reads the
+        #      solution and the statistics back (set_initial_state! / update_trajectory! / solve! / states / stats)
+        sv.restore()
+        sv.fetch()  # host mirror of X, U at the snapshot
+        wl.k = k_snap.copy()
+        prob.kidx[...] = wl.k if wl.track is not None or name == "grasp" else prob.kidx
+        t_api, h2d_s, d2h_s = 0.0, 0, prob.X.nbytes + prob.U.nbytes + B * (4 * 4 + 4 * 8 + 8)
+        for st in range(K):
+            z = zs_all[W + st]
+            if wl.track is not None and prob.model.sched is None:
+                # host side of the reference's loop (plant step + noise, window of the tracked trajectory): the caller's work
+                x0 = wl.apply_noise(prob.X[:, 1, :], z)
+                wl.k = wl.k + 1
+                Xr, Ur = mpc.window_reference(wl.track[0], wl.track[1], wl.k, prob.N)
+                t0 = time.perf_counter()
+                prob.kidx += 1
+                if name == "grasp":
+                    sv.set_track_index(prob.kidx)
+                prob.set_initial_state(x0)      # H2D x0
+                prob.update_trajectory(Xr, Ur)   # H2D reference window
+                if wl.shift:
+                    sv.shift_fill(True, True)
+                sv.solve(fetch=True)             # solve! + D2H X, U, statistics
+                t_api += time.perf_counter() - t0
+                h2d_s = x0.nbytes + Xr.nbytes + Ur.nbytes
+            else:
+                # gait-scheduled / untracked workloads: the step's disturbance goes up, the device does the plant step
+                zz = np.ascontiguousarray(z)
+                t0 = time.perf_counter()
+                sv.mpc_transition(zz, shift=wl.shift)  # H2D disturbance
+                sv.solve(fetch=True)                   # solve! + D2H X, U, statistics
+                t_api += time.perf_counter() - t0
+                h2d_s = zz.nbytes
+        barrier()
+        t_api = sharding.max_over_ranks(t_api)
+        per_step["e2e"] = {"value": B * world * K / t_api, "unit": UNIT, "h2d_bytes_per_step": int(h2d_s),
+                           "d2h_bytes_per_step": int(d2h_s), "ms_per_step": 1e3 * t_api / K}
+
+    achieved = flops / kern_s / 1e12
+    alg_bytes = algorithmic_bytes(prob, sv.P)
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tnote = "no ncu capture for this workload / batch"
+    tfile = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tfile):  # DRAM bytes per launch from the committed ncu --set full capture of this kernel
+        tj = json.load(open(tfile)).get(name)
+        if tj and tj.get("batch") == B and tj.get("kernel") == info.get("kernel"):
+            traffic = tj["per_launch_fixed"] + tj["per_step"] * K
+            tnote = tj["source"]
+    res = {
+        "value": B * world * K / total_s, "unit": UNIT, "ms_per_step": 1e3 * total_s / K,
+        "config": {"workload": wl.desc, "instances_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"instance-sharded x{world}, no collective on the solve path",
+                   "l2": f"L2 flushed before every timed launch ({L2_FLUSH_BYTES >> 20} MB write)",
+                   "launch": info,
+                   "step": "closed-loop MPC run: per instance K x {transition + shift_fill + AL-iLQR solve} in one "
+                           "launch, instances advance independently"},
+        "p50_solve_us": float(np.median(rr["t_us"])), "max_solve_us": float(rr["t_us"].max()),
+        "iters_mean": float(rr["iterations"].mean()), "iters_max": int(rr["iterations"].max()),
+        "ls_trials_mean": float(rr["ls_trials"].mean()),
+        "success": float(np.mean(rr["status"] == 1)), "status_counts": status_counts,
+        "success_all_ranks_last_step": float(np.mean(gathered["status"] == 1)),
+        "iters_all_ranks_last_step": float(np.mean(gathered["iterations"])),
+        "init_success": init_ok,
+        "gpu_launches": 2,  # altro_{lane,solve}_kernel + advance_kidx_kernel inside the timed region
+        "steps_per_launch": K,
+        "clocks": sampler.summary(),
+        # "tensor" = the compute roofline of the two the contract names; here it is the FP64 one (DFMA, DMMA m8n8k4 for
+        # the CTA kernels).  The kernels are latency / issue bound, not pipe bound: see `limiter`.
+        "roofline": {"bound": "tensor", "pipe": "fp64", "achieved": achieved, "peak": peaks["dfma_tflops"],
+                     "unit": "TFLOP/s", "frac": achieved / peaks["dfma_tflops"], "traffic": traffic,
+                     "traffic_note": tnote,
+                     "limiter": "dependent-instruction latency and issue slots (profiles/r2_summary.md), not the FP64 pipe",
+                     "peak_source": "DFMA stream measured live by altro_measure_peaks in this run "
+                                    "(MEASURED_PEAKS.json has no FP64 figure); DMMA m8n8k4 peak "
+                                    f"{peaks['dmma_tflops']:.1f} TFLOP/s",
+                     "kernel": "altro_lane_kernel" if info.get("kernel") == "lane" else "altro_solve_kernel",
+                     "kernel_ms_per_step": 1e3 * kern_s / K,
+                     "kernel_share_of_step": kern_s / step_s,
+                     "flops_per_step": flops / K,
+                     "hbm": {"achieved": alg_bytes * B * K / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes * B * K / kern_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                             "algorithmic_bytes_per_solve": alg_bytes}},
+        "wall_s_timed_region": wall,
+        "per_step_api": per_step,
+        "lockstep": {k: per_step[k] for k in ("value", "unit", "ms_per_step", "note")},
+    }
+    if e2e:
+        res["e2e"] = e2e
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        nt = host_threads()
+        cpu_steps = args.cpu_steps
+        if cpu_steps <= 0:  # probe 4 steps, then size the sample for about 20 core-seconds (bounded by K)
+            probe = oracle_arm(Workload(name, args.batch, seed, make_solver), 4, 1, nt)
+            cpu_steps = int(min(max(4, round(20.0 / nt * probe["value"] / B)), max(K, 4)))
+        r = oracle_arm(Workload(name, args.batch, seed, make_solver), cpu_steps, 1, nt)
+        res["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": nt, "kind": "port",
+                               "sample": f"{cpu_steps} MPC steps x {B} instances of the same workload, CPU oracle "
+                                         f"(oracle/altro_oracle.c, pthreads over instances), {r['seconds']:.2f} s",
+                               "iters_mean": r["iters_mean"]}
+    sv.close()
+    return res
+
+
+def reference_workload(name, args, K, W, seed):
+    """The reference arm of one workload: the CPU oracle (port) on all host threads, whole batch per step."""
+    from oracle.oracle import OracleProblem
+
+    class _OS:
+        def __init__(self, prob, opts):
+            self.prob, self.opts, self.op = prob, opts, OracleProblem(prob)
+
+        def solve(self):
+            self.stats = self.op.solve(self.opts, nthreads=1)
+            return self
+
+    wl = Workload(name, args.batch, seed, _OS)
+    nt = host_threads()
+    r = oracle_arm(wl, K, W, nt)
+    return {"value": r["value"], "unit": UNIT, "ms_per_step": 1e3 * r["seconds"] / K,
+            "config": {"workload": wl.desc, "batch_per_step": wl.batch, "parallelism": f"{nt} host threads",
+                       "note": "the CPU arm solves `batch_per_step` instances per step whatever --gpus says; the GPU arm "
+                               "solves that many PER GPU (weak scaling): compare throughputs"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": nt, "kind": "port",
+                             "sample": f"{K} MPC steps x {wl.batch} instances (whole batch), CPU oracle "
+                                       f"oracle/altro_oracle.c, pthreads over instances"},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "iters_mean": r["iters_mean"], "success": r["success"]}
+
+
 # ----------------------------------------------------------------------------- main
 
 
@@ -265,7 +459,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100, help="MPC steps timed (the reference's loops run 100-280)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rocket")
+    ap.add_argument("--workload", default=None, help="headline workload (default rocket, with quadruped as secondary)")
+    ap.add_argument("--secondary", default=None, help="comma-separated secondary workloads (default: quadruped)")
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     ap.add_argument("--threads-per-instance", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=0,
@@ -275,41 +470,22 @@ def main():
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 0)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    seed = 0xA1720 + 2 + 1000 * rank
+    headline = args.workload or os.environ.get("ALTRO_BENCH_WORKLOAD") or "rocket"
+    if args.secondary is not None:
+        secondary = [w for w in args.secondary.split(",") if w]
+    else:
+        secondary = ["quadruped"] if args.workload is None and "ALTRO_BENCH_WORKLOAD" not in os.environ else []
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
 
     if args.impl == "reference":
         if rank != 0:
             return  # rank 0 alone runs the CPU arm
-        wl_builder_solver = None
-        try:
-            import torch
-
-            have_gpu = torch.cuda.is_available()
-        except Exception:
-            have_gpu = False
-        # the rocket workload needs the cold-solved track; the CPU arm computes it with the oracle itself
-        from oracle.oracle import OracleProblem
-
-        class _OS:
-            def __init__(self, prob, opts):
-                self.prob, self.opts, self.op = prob, opts, OracleProblem(prob)
-
-            def solve(self):
-                self.stats = self.op.solve(self.opts, nthreads=1)
-                return self
-
-        wl = Workload(args.workload, args.batch, seed, _OS)
-        nt = host_threads()
-        r = oracle_arm(wl, K, W, nt)
-        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": K, "warmup": W, "ms_per_step": 1e3 * r["seconds"] / K, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl.desc, "batch_per_step": wl.batch, "parallelism": f"{nt} host threads"},
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": nt, "kind": "port",
-                                 "sample": f"{K} MPC steps x {wl.batch} instances (whole batch), CPU oracle "
-                                           f"oracle/altro_oracle.c, pthreads over instances"},
-                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "iters_mean": r["iters_mean"], "success": r["success"]}
+        seed = 0xA1720 + 2
+        line = dict(base, impl="reference")
+        line.update(reference_workload(headline, args, K, W, seed))
+        if secondary:
+            line["workloads"] = {w: reference_workload(w, args, K, W, seed) for w in secondary}
         print(json.dumps(line))
         return
 
@@ -330,210 +506,25 @@ def main():
     def make_solver(prob, opts, **kw):
         return S.ALTROSolver(prob, opts, device=local, stream=stream.cuda_stream, **kw)
 
-    wl = Workload(args.workload, args.batch, seed, make_solver)
-    prob, B = wl.prob, wl.batch
-    sv = make_solver(prob, wl.opts, threads_per_instance=args.threads_per_instance, pin=True)
-    if wl.track is not None:
-        sv.set_track(wl.track[0], wl.track[1], wl.k)  # before the first launch: the window is then read from the track
-    info = sv.launch_info()
-    peaks = S.measure_peaks(local)
-    sv.set_noise_model(*wl.noise_model)
-    zs_all = wl.noise_samples(max(W, 1) + K)
-    sv.set_noise_bank(zs_all)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    qrng = mpc.rng_for(seed, 77)
-    fused = wl.qstate is None  # closed-loop run in one launch; quadruped rebuilds B_k on the host every tick
-    S_launch = K if fused else 1
-
-    def q_tick(fetch):
-        quadruped.advance(prob, wl.qstate, qrng)
-        sv.upload()
-        sv.shift_fill(True, True)
-        sv.solve(fetch=fetch)
-
-    # ---- initial solve + warm-up (untimed)
-    sv.solve()
-    init_ok = float(np.mean(sv.stats.status == 1))
-    if fused:
-        if W:
-            sv.mpc_run(W, shift=wl.shift)
-    else:
-        for _ in range(W):
-            q_tick(True)
-    if fused:
-        sv.reserve_steps(K)  # log buffers sized before the timed region (no cudaFree/cudaMalloc inside it)
-        sv.snapshot()  # the lock-step and e2e phases replay the same K steps from this state
-    barrier()
-    # ---- timed region: K steps, CUDA events on the launching stream around every launch
-    sampler = ClockSampler(local)
-    sampler.start()
-    n_launch = K // S_launch
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_launch)]
-    kern_ms, flops, per_step = [], 0.0, []
-    t_wall = time.perf_counter()
-    for li in range(n_launch):
-        flush.zero_()  # L2 flush between timed launches (256 MB write, outside the event pair)
-        if fused:
-            ev[li][0].record(stream)
-            sv.mpc_run(S_launch, shift=wl.shift, fetch=False)
-            ev[li][1].record(stream)
-            rr = sv.run_results(S_launch)  # D2H after the event pair: needed for the flop model, not timed
-            kern_ms.append(rr["device_ms"])
-            flops += flops_model(prob, rr["iterations"], rr["iterations_outer"], rr["ls_trials"])
-            for st in range(S_launch):
-                per_step.append((float(rr["iterations"][st].mean()), float(rr["ls_trials"][st].mean()),
-                                 float(np.mean(rr["status"][st] == 1)), float(np.median(rr["t_us"][st])),
-                                 float(rr["t_us"][st].max())))
-            last_status, last_iters = rr["status"][-1], rr["iterations"][-1]
-        else:
-            quadruped.advance(prob, wl.qstate, qrng)
-            sv.upload()
-            ev[li][0].record(stream)
-            sv.shift_fill(True, True)
-            sv.solve(fetch=False)
-            ev[li][1].record(stream)
-            stt = sv.fetch()
-            kern_ms.append(stt.tsolve)
-            flops += flops_model(prob, stt.iterations, stt.iterations_outer, stt.ls_trials)
-            per_step.append((float(stt.iterations.mean()), float(stt.ls_trials.mean()), float(np.mean(stt.status == 1)),
-                             float(np.median(stt.t_instance_us)), float(stt.t_instance_us.max())))
-            last_status, last_iters = stt.status, stt.iterations
-    barrier()
-    wall = time.perf_counter() - t_wall
-    sampler.stop_flag.set()
-    sampler.join()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_s = sharding.max_over_ranks(sum(step_ms) * 1e-3)
-    kern_s = sum(kern_ms) * 1e-3
-    gathered = sharding.gather_stats({"iterations": last_iters, "status": last_status})
-
-    # ---- lock-step variant for the record: one transition + one solve launch per MPC step (every step waits
-    #      for the slowest instance of the batch)
-    lock = None
-    if fused:
-        sv.restore()
-        evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for st in range(K):
-            flush.zero_()
-            evl[st][0].record(stream)
-            sv.mpc_transition(None, shift=wl.shift)
-            sv.solve(fetch=False)
-            evl[st][1].record(stream)
-        barrier()
-        t_lock = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evl) * 1e-3)
-        lock = {"value": B * world * K / t_lock, "unit": UNIT, "ms_per_step": 1e3 * t_lock / K,
-                "note": "one launch per MPC step: each step waits for the slowest instance"}
-        sv.fetch()
-
-    # ---- e2e: same metric through the public API with host buffers
-    e2e = None
-    if not args.no_e2e:
-        barrier()
-        if fused:
-            sv.restore()
-            zs = np.ascontiguousarray(zs_all[W:W + K])  # the same disturbances the device-timed run consumed
-            sv.lib.altro_host_register(S._p(zs), zs.nbytes)
-            h2d = zs.nbytes
-            d2h = K * B * (prob.n + prob.m) * 8 + K * B * (4 * 4 + 2 * 8 + 8) + prob.X.nbytes + prob.U.nbytes
-            t0 = time.perf_counter()
-            sv.set_noise_bank(zs)  # H2D of this run's inputs
-            sv.mpc_run(K, shift=wl.shift, fetch=True)  # run + D2H of closed-loop states, controls, statistics, X, U
-            t_e2e = time.perf_counter() - t0
-            sv.lib.altro_host_unregister(S._p(zs))
-            h2d, d2h = h2d / K, d2h / K
-        else:
-            h2d = prob.x0.nbytes + prob.model.A.nbytes + prob.model.B.nbytes + prob.model.d.nbytes
-            d2h = prob.X.nbytes + prob.U.nbytes + B * (4 * 4 + 4 * 8 + 8)
-            t_e2e = 0.0
-            for st in range(K):
-                quadruped.advance(prob, wl.qstate, qrng)  # host-side linearisation (the caller's work, not timed)
-                t0 = time.perf_counter()
-                sv.shift_fill(True, True)  # pinned H2D of x0 and A_k, B_k, d_k, then the shifts on the device
-                sv.solve(fetch=True)  # solve + D2H of X, U and statistics
-                t_e2e += time.perf_counter() - t0
-        barrier()
-        t_e2e = sharding.max_over_ranks(t_e2e)
-        e2e = {"value": B * world * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / K}
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    value = B * world * K / total_s
-    achieved = flops / kern_s / 1e12
-    bytes_alg = algorithmic_bytes(prob, sv.P) * B * K
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        hbm_src = "MEASURED_PEAKS.json"
-    except Exception:
-        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-    ps = np.array(per_step)
-    traffic = None
-    if wl.name == "rocket" and B == 4096 and fused:
-        # 23.66 MB for the 20-step launch (ncu, profiles/r1_solve_kernel_ncu_metrics.json): per launch the state of the
-        # run, track and constraint data in and the solution out (18.7 MB), per step 4096 x 48 B of disturbances in
-        # and the step's closed-loop log and statistics out (0.25 MB); scaled to this launch's step count
-        traffic = 18.7e6 + 0.25e6 * S_launch
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * total_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.desc, "instances_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"instance-sharded x{world}, no collective on the solve path",
-                   "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MB write)",
-                   "launch": info,
-                   "step": ("closed-loop MPC run: per instance K x {transition + shift_fill + AL-iLQR solve} in one "
-                            "launch, instances advance independently") if fused else
-                           "host-built dynamics upload + device shift_fill + batched AL-iLQR solve, one launch per step"},
-        "p50_solve_us": float(np.median(ps[:, 3])), "max_solve_us": float(ps[:, 4].max()),
-        "iters_mean": float(ps[:, 0].mean()), "ls_trials_mean": float(ps[:, 1].mean()),
-        "success": float(ps[:, 2].mean()), "success_all_ranks_last_step": float(np.mean(gathered["status"] == 1)),
-        "iters_all_ranks_last_step": float(np.mean(gathered["iterations"])),
-        "init_success": init_ok,
-        "gpu_launches": int(2 * n_launch if fused else 2 * K),
-        "steps_per_launch": S_launch,
-        "clocks": sampler.summary(),
-        # "tensor" = the compute roofline of the two the contract names; here it is the FP64 one (DFMA + DMMA m8n8k4)
-        "roofline": {"bound": "tensor", "pipe": "fp64", "achieved": achieved, "peak": peaks["dfma_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["dfma_tflops"], "traffic": traffic,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the "
-                                     "20-step rocket launch (profiles/r1_summary.md), scaled to this launch's step count",
-                     "peak_source": "DFMA stream measured live by altro_measure_peaks in this run "
-                                    "(MEASURED_PEAKS.json has no FP64 figure); DMMA m8n8k4 peak "
-                                    f"{peaks['dmma_tflops']:.1f} TFLOP/s",
-                     "kernel": "altro_solve_kernel", "kernel_ms_per_step": 1e3 * kern_s / K,
-                     "kernel_share_of_step": kern_s / (sum(step_ms) * 1e-3),
-                     "flops_per_step": flops / K,
-                     "hbm": {"achieved": bytes_alg / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": bytes_alg / kern_s / 1e9 / hbm_peak, "peak_source": hbm_src,
-                             "algorithmic_bytes_per_solve": algorithmic_bytes(prob, sv.P)}},
-        "wall_s_timed_region": wall,
-    }
-    if e2e:
-        line["e2e"] = e2e
-    if lock:
-        line["lockstep"] = lock
-    if world == 1 and not args.no_cpu_baseline:
-        nt = host_threads()
-        cpu_steps = args.cpu_steps
-        if cpu_steps <= 0:  # probe 4 steps, then size the sample for about 20 core-seconds (bounded by K)
-            probe = oracle_arm(Workload(args.workload, args.batch, seed, make_solver), 4, 1, nt)
-            cpu_steps = int(min(max(4, round(20.0 / nt * probe["value"] / B)), max(K, 4)))
-        r = oracle_arm(Workload(args.workload, args.batch, seed, make_solver), cpu_steps, 1, nt)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": nt, "kind": "port",
-                                "sample": f"{cpu_steps} MPC steps x {B} instances of the same workload, CPU oracle "
-                                          f"(oracle/altro_oracle.c, pthreads over instances), {r['seconds']:.2f} s",
-                                "iters_mean": r["iters_mean"]}
-    print(json.dumps(line))
+    peaks = S.measure_peaks(local)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    results = {}
+    for name in [headline] + secondary:
+        results[name] = bench_gpu_workload(name, args, K, W, rank, world, local, stream, dev, flush, peaks, make_solver,
+                                           barrier, S, sharding)
+    if rank == 0:
+        line = dict(base)
+        line.update(results[headline])
+        line["n_gpus"] = world
+        if secondary:
+            line["workloads"] = {w: results[w] for w in secondary}
+            line["gpu_launches"] = sum(results[w]["gpu_launches"] for w in results)
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -200,11 +200,17 @@ int altro_host_unregister(void *ptr);
 /* Launch geometry of the solve kernel: threads per instance, dynamic shared memory bytes per
  * instance (CTA), registers per thread, resident CTAs per SM. threads=0 in the setter = automatic. */
 int altro_set_launch_config(altro_handle_t h, int threads_per_instance);
-/* Which kernel runs solve!: 1 = one CTA per instance (any dimensions), 2 = one thread per instance, a warp advancing
- * 32 instances (small dimensions: rocket 6/3, grasp 6/6), 0 = automatic (lane kernel where one exists, unless a CTA
- * geometry was asked for).  Results are bit-identical either way.  The getter reports the kernel in use. */
+/* Which kernel runs solve!: 1 = one CTA per instance (any dimensions; the default), 2 = one thread per instance, a
+ * warp advancing 8 instances (small dimensions with a shared LTI model: rocket 6/3, grasp 6/6; an experiment that
+ * measured slower, see csrc/altro_lane.cuh), 0 = automatic (= 1).  Results are bit-identical either way.  The getter
+ * reports the kernel in use. */
 int altro_set_kernel_mode(altro_handle_t h, int mode);
-int altro_get_kernel_mode(altro_handle_t h, int *mode, int *lane_regs_per_thread, int *lane_smem_bytes);
+/* Scheduling of altro_mpc_run: steps_per_item >= 1 (default 1) runs it on a persistent grid whose CTAs pull
+ * (instance, steps_per_item consecutive steps) work items from an atomic queue, so that no slot idles while another
+ * still owns long chains; 0 = one CTA per instance for the whole run.  Same results either way. */
+int altro_set_run_queue(altro_handle_t h, int steps_per_item);
+int altro_get_kernel_mode(altro_handle_t h, int *mode, int *lane_regs_per_thread, int *lane_smem_bytes,
+                          int *instances_per_warp);
 int altro_get_launch_info(altro_handle_t h, int *threads_per_instance, int *smem_bytes, int *regs_per_thread,
                           int *ctas_per_sm, int *num_sms);
 

@@ -14,9 +14,14 @@ using namespace altro;
 template <int NX, int NU>
 static void run_all(const Params &P, const LaneLayout &L, int B)
 {
-    std::vector<double> ws((size_t)L.total * B, 0.0), scr(LANE_SCRATCH, 0.0);
+    std::vector<double> ws((size_t)L.total * B, 0.0), scr(LANE_SCRATCH + P.N * (1 + P.ncon), 0.0);
+    LaneConst<NX, NU> C;
+    for (int i = 0; i < NX * NX; ++i) C.A[i] = P.A[i];
+    for (int i = 0; i < NX * NU; ++i) C.B[i] = P.Bm[i];
+    for (int i = 0; i < NX; ++i) { C.d[i] = P.d[i]; C.Q[i] = P.Q[i]; C.Qf[i] = P.Qf[i]; }
+    for (int i = 0; i < NU; ++i) C.R[i] = P.R[i];
     for (int i = 0; i < B; ++i) {
-        Lane<NX, NU> ln(P, L, ws.data() + i, (size_t)B, scr.data(), 1, i);
+        Lane<NX, NU, 1> ln(P, C, L, ws.data() + i, (size_t)B, scr.data(), P.con, i);
         ln.load();
         while (ln.phase != LP_DONE) ln.step();
         ln.store();

@@ -113,7 +113,7 @@ def test_speculative_line_search_does_not_change_bits(family, spec, threads):
     assert np.array_equal(g.stats.ls_trials, o.stats.ls_trials)
 
 
-@pytest.mark.parametrize("batch", [1, 31, 33, 200])
+@pytest.mark.parametrize("batch", [1, 7, 33, 200])
 def test_lane_kernel_matches_oracle_and_cta_kernel(batch):
     """One thread per instance (altro_lane.cuh) vs one CTA per instance vs the oracle: same bits, any batch size
     (partial warps included)."""
@@ -128,13 +128,11 @@ def test_lane_kernel_matches_oracle_and_cta_kernel(batch):
     assert o.stats.iterations.max() > 2
 
 
-def test_lane_kernel_is_the_default_for_small_dimensions_only():
+def test_lane_kernel_is_opt_in_and_limited_to_small_shared_lti_problems():
     cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
     prob, opts, _, _ = cases.case_rocket_mpc(cold["X"], cold["U"], batch=64)
-    assert gpu_solver(prob, opts).launch_info()["kernel"] == "lane"
-    small, _, _, _ = cases.case_rocket_mpc(cold["X"], cold["U"], batch=8)
-    assert gpu_solver(small, opts).launch_info()["kernel"] == "cta"  # a few instances: one CTA each
-    assert gpu_solver(copy.deepcopy(prob), opts, threads_per_instance=64).launch_info()["kernel"] == "cta"
+    assert gpu_solver(prob, opts).launch_info()["kernel"] == "cta"
+    assert gpu_solver(copy.deepcopy(prob), opts, kernel="lane").launch_info()["kernel"] == "lane"
     pq, oq, _, _ = cases.case_quadruped(True, batch=4)
     assert gpu_solver(pq, oq).launch_info()["kernel"] == "cta"
     from altro_mpc_icra2021_b200.solver import AltroError
@@ -470,6 +468,32 @@ def test_closed_loop_run_matches_oracle_and_stepwise_path(family):
     assert np.array_equal(ps.X, pg.X) and np.array_equal(ps.U, pg.U)
     # and the run can be continued: two runs of 2 + 3 steps equal one of 5
     pc = copy.deepcopy(prob)  # prob was advanced by the oracle run; rebuild the starting point instead
+
+
+@pytest.mark.parametrize("chunk", [0, 1, 3, 100])
+def test_closed_loop_run_scheduling_does_not_change_bits(chunk):
+    """Persistent grid + work queue of (instance, chunk of steps) items vs one CTA per instance for the whole run."""
+    B, steps = 300, 7
+    cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+    Xt, Ut = cold["X"], cold["U"]
+    prob, opts, _, _ = cases.case_rocket_mpc(Xt, Ut, batch=B)
+    ks = mpc.rng_for(11, 0).integers(0, Xt.shape[0] - 21 - 110, size=B)
+    noise = mpc.rng_for(3, 3).standard_normal((steps, B, prob.n))
+    pg = copy.deepcopy(prob)
+    o = OracleSolver(prob, opts, nthreads=8).solve()
+    g = gpu_solver(pg, opts).solve()
+    g.set_run_queue(chunk)
+    g.set_track(Xt, Ut, ks)
+    g.set_noise_model(2, 1e-3, 1e-2)
+    g.set_noise_bank(noise)
+    rg = g.mpc_run(steps)
+    ro = o.op.mpc_run(opts, steps, noise, (2, 1e-3, 1e-2), (Xt, Ut), ks, True, nthreads=8)
+    for k in ro:
+        assert np.array_equal(rg[k], ro[k]), k
+    assert np.array_equal(pg.X, prob.X) and np.array_equal(pg.U, prob.U) and np.array_equal(g.get_duals(), o.op.lam)
+    rg2 = g.mpc_run(2)  # and again from where it stopped
+    ro2 = o.op.mpc_run(opts, 2, noise[:2], (2, 1e-3, 1e-2), (Xt, Ut), ks + steps, True, nthreads=8)
+    assert np.array_equal(rg2["x0"], ro2["x0"]) and np.array_equal(rg2["iterations"], ro2["iterations"])
 
 
 @pytest.mark.parametrize("linearized", [True, False])
