@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,8 @@
 #include <vector>
 
 #include "altro_lane.cuh"
+#include "altro_quadruped.cuh"
+#include "altro_admm.cuh"
 
 using namespace altro;
 
@@ -85,6 +88,13 @@ struct altro_handle_s {
     Layout lay;
     int spec = 0, spec_req = -1;  // speculative line search: in use / requested (-1 = automatic)
     // lane-per-instance kernel (altro_lane.cuh): small dimensions, one thread per instance
+    // convex cross-check (admm.cu): workspace and outputs
+    double *admm_ws = nullptr, *admm_X = nullptr, *admm_U = nullptr, *admm_rp = nullptr, *admm_rd = nullptr;
+    int *admm_it = nullptr;
+    // quadruped pre-solve kernels (quadruped.cu): device scratch, footstep-planner state
+    double *q_xref = nullptr, *q_uref = nullptr, *q_foot = nullptr, *q_contacts = nullptr, *q_t = nullptr,
+           *q_curfoot = nullptr, *q_planner = nullptr;
+    bool q_planner_set = false;
     int run_chunk = 1;    // closed-loop runs: steps per work item of the persistent grid (0 = one CTA per instance)
     int *q_ctrl = nullptr;  // [2 + B]: queue head, error flag, per-instance completed steps
     int kernel_mode = 0;  // 0 automatic, 1 CTA per instance, 2 lane per instance
@@ -607,7 +617,7 @@ int altro_destroy(altro_handle_t h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *ptrs[] = {h->A, h->Bm, h->d, h->Q, h->R, h->Qf, h->xref, h->uref, h->x0, h->X, h->U, h->lam, h->X_snap,
                     h->U_snap, h->lam_snap, h->x0_snap, h->xref_snap, h->uref_snap, h->kidx_snap, h->iters, h->outer, h->status, h->trials, h->cost, h->cost_al, h->cmax,
-                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->ws, h->lane_ws, h->q_ctrl, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
+                    h->penmax, h->t_ns, h->x0_log, h->u0_log, h->phase, h->trace, h->con_dev, h->itab_dev, h->sched, h->ex_glob, h->ws, h->lane_ws, h->q_ctrl, h->admm_ws, h->admm_X, h->admm_U, h->admm_rp, h->admm_rd, h->admm_it, h->q_xref, h->q_uref, h->q_foot, h->q_contacts, h->q_t, h->q_curfoot, h->q_planner, h->trackX, h->trackU, h->noise, h->noise_bank, h->kidx};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &c : h->cons) {
@@ -1271,6 +1281,176 @@ int altro_mpc_transition(altro_handle_t h, const double *noise, int shift)
     }
     if (shift) return altro_shift_fill(h, 1, 1);
     return ALTRO_OK;
+}
+
+// ---- independent convex cross-check on the device (admm.cu)
+
+int altro_admm_solve(altro_handle_t h, double rho, double eps, int max_iter, double *X, double *U, int *iterations,
+                     double *r_prim, double *r_dual)
+{
+    REQ(h);
+    int rc = finalize(h);
+    if (rc) return rc;
+    if (!(rho > 0.0) || !(eps > 0.0) || max_iter < 1) return fail(h, ALTRO_ERR_INVALID, "bad ADMM parameters");
+    if (!h->have_x0) return fail(h, ALTRO_ERR_STATE, "x0 not set");
+    for (auto &c : h->cons)
+        if (c.sense == ALTRO_SECOND_ORDER_CONE && c.p > PMAX_ADMM) return fail(h, ALTRO_ERR_UNSUPPORTED, "cone with more than 8 rows");
+    const size_t B = h->B, n = h->n, m = h->m, N = h->N;
+    const size_t wsd = admm_workspace_doubles(h->n, h->m, h->N, h->P);
+    if (!h->admm_ws) {
+        CK(h, dalloc(&h->admm_ws, B * wsd));
+        CK(h, dalloc(&h->admm_X, B * N * n)); CK(h, dalloc(&h->admm_U, B * (N - 1) * m));
+        CK(h, dalloc(&h->admm_rp, B)); CK(h, dalloc(&h->admm_rd, B)); CK(h, dalloc(&h->admm_it, B));
+    }
+    AdmmParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = h->n; P.m = h->m; P.N = h->N; P.B = h->B; P.Pd = h->P; P.ncon = (int)h->cons.size();
+    P.dt = h->dt; P.rho = rho; P.eps = eps; P.max_iter = max_iter; P.adapt = 25;
+    P.dyn_per_knot = h->dyn_per_knot; P.dyn_per_instance = h->dyn_per_instance; P.dyn_slots = h->dyn_slots;
+    P.sched_len = h->sched_len; P.step0 = h->step_abs; P.dyn_sched = h->sched; P.kidx = h->kidx;
+    P.A = h->A; P.Bm = h->Bm; P.d = h->d; P.Q = h->Q; P.R = h->R; P.Qf = h->Qf;
+    P.xref = h->xref; P.uref = h->uref; P.x0 = h->x0; P.X = h->X; P.U = h->U;
+    P.con = h->con_dev; P.ws = h->admm_ws; P.ws_doubles = wsd;
+    P.Xout = h->admm_X; P.Uout = h->admm_U; P.rprim = h->admm_rp; P.rdual = h->admm_rd; P.iters = h->admm_it;
+    CK(h, admm_launch(P, h->stream));
+    if (X) rc |= download(h, X, h->admm_X, B * N * n * sizeof(double));
+    if (U) rc |= download(h, U, h->admm_U, B * (N - 1) * m * sizeof(double));
+    if (iterations) rc |= download(h, iterations, h->admm_it, B * sizeof(int));
+    if (r_prim) rc |= download(h, r_prim, h->admm_rp, B * sizeof(double));
+    if (r_dual) rc |= download(h, r_dual, h->admm_rd, B * sizeof(double));
+    if (rc) return ALTRO_ERR_CUDA;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return ALTRO_OK;
+}
+
+// ---- quadruped: the step before the solve path, on the device (quadruped.cu)
+
+static int quad_prepare(altro_handle_t h)
+{
+    if (h->n != 12 || h->m != 12) return fail(h, ALTRO_ERR_INVALID, "quadruped kernels need n = m = 12");
+    const size_t B = h->B, K = h->N - 1, cnt = B * K;
+    if (h->have_dyn && (h->dyn_count != cnt || !h->dyn_per_knot || !h->dyn_per_instance || h->sched)) {
+        if (h->finalized) return fail(h, ALTRO_ERR_STATE, "dynamics layout cannot change after the first solve");
+        cudaFree(h->A); cudaFree(h->Bm); cudaFree(h->d);
+        h->A = h->Bm = h->d = nullptr;
+        h->have_dyn = false;
+    }
+    if (!h->have_dyn) {
+        CK(h, dalloc(&h->A, cnt * 144));
+        CK(h, dalloc(&h->Bm, cnt * 144));
+        CK(h, dalloc(&h->d, cnt * 12));
+        h->dyn_count = cnt; h->dyn_per_knot = 1; h->dyn_per_instance = 1;
+        h->have_dyn = true;
+        h->hA.clear();
+    }
+    if (!h->q_xref) {
+        CK(h, dalloc(&h->q_xref, cnt * 12)); CK(h, dalloc(&h->q_uref, cnt * 12)); CK(h, dalloc(&h->q_foot, cnt * 12));
+        CK(h, dalloc(&h->q_contacts, cnt * 4)); CK(h, dalloc(&h->q_t, B)); CK(h, dalloc(&h->q_curfoot, B * 12));
+        CK(h, dalloc(&h->q_planner, B * 12));
+    }
+    return ALTRO_OK;
+}
+
+static int quad_body(altro_handle_t h, const double *J, double mass, QuadrupedBody *body)
+{
+    if (!J || !(mass > 0.0)) return fail(h, ALTRO_ERR_INVALID, "bad inertia / mass");
+    for (int i = 0; i < 9; ++i) body->J[i] = J[i];
+    const double *a = J;
+    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    if (!(fabs(det) > 0.0)) return fail(h, ALTRO_ERR_INVALID, "singular inertia");
+    const double id = 1.0 / det;
+    body->Jinv[0] = (a[4] * a[8] - a[5] * a[7]) * id; body->Jinv[1] = (a[2] * a[7] - a[1] * a[8]) * id; body->Jinv[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    body->Jinv[3] = (a[5] * a[6] - a[3] * a[8]) * id; body->Jinv[4] = (a[0] * a[8] - a[2] * a[6]) * id; body->Jinv[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    body->Jinv[6] = (a[3] * a[7] - a[4] * a[6]) * id; body->Jinv[7] = (a[1] * a[6] - a[0] * a[7]) * id; body->Jinv[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+    body->mass = mass;
+    return ALTRO_OK;
+}
+
+int altro_quadruped_linearize(altro_handle_t h, const double *x_ref, int x_ref_per_knot, const double *u_ref,
+                              int u_ref_per_knot, const double *foot, const double *contacts, const double *J,
+                              double mass)
+{
+    REQ(h);
+    if (!x_ref || !foot || !contacts) return fail(h, ALTRO_ERR_INVALID, "null quadruped inputs");
+    int rc = quad_prepare(h);
+    if (rc) return rc;
+    QuadrupedBody body;
+    rc = quad_body(h, J, mass, &body);
+    if (rc) return rc;
+    const size_t B = h->B, K = h->N - 1;
+    rc = upload(h, h->q_xref, x_ref, B * (x_ref_per_knot ? K : 1) * 12);
+    if (!rc && u_ref) rc = upload(h, h->q_uref, u_ref, B * (u_ref_per_knot ? K : 1) * 12);
+    if (!rc) rc = upload(h, h->q_foot, foot, B * K * 12);
+    if (!rc) rc = upload(h, h->q_contacts, contacts, B * K * 4);
+    if (rc) return rc;
+    CK(h, quadruped_linearize_launch((int)B, (int)K, h->q_xref, x_ref_per_knot, u_ref ? h->q_uref : nullptr, u_ref_per_knot,
+                                     h->q_foot, h->q_contacts, body, h->dt, h->A, h->Bm, h->d, h->stream));
+    return ALTRO_OK;
+}
+
+int altro_quadruped_tick(altro_handle_t h, const double *t, const double *x_ref, int x_ref_per_knot,
+                         const double *cur_foot, int num_phases, const double *contact_phases,
+                         const double *phase_times, double alpha, double foot_radius, const double *nom_foot,
+                         const double *J, double mass)
+{
+    REQ(h);
+    if (!t || !x_ref || !cur_foot || !contact_phases || !phase_times || !nom_foot || num_phases < 1 || num_phases > 8)
+        return fail(h, ALTRO_ERR_INVALID, "bad gait description");
+    int rc = quad_prepare(h);
+    if (rc) return rc;
+    QuadrupedBody body;
+    rc = quad_body(h, J, mass, &body);
+    if (rc) return rc;
+    QuadrupedGait g;
+    memset(&g, 0, sizeof(g));
+    g.num_phases = num_phases;
+    g.phase_length = 0.0;
+    for (int i = 0; i < num_phases; ++i) {
+        g.phase_times[i] = phase_times[i];
+        g.phase_length += phase_times[i];
+        for (int j = 0; j < 4; ++j) g.contact[i * 4 + j] = contact_phases[i * 4 + j];
+    }
+    g.alpha = alpha; g.foot_radius = foot_radius;
+    for (int i = 0; i < 12; ++i) g.nom_foot[i] = nom_foot[i];
+    const size_t B = h->B, K = h->N - 1;
+    rc = upload(h, h->q_t, t, B);
+    if (!rc) rc = upload(h, h->q_xref, x_ref, B * (x_ref_per_knot ? K : 1) * 12);
+    if (!rc) rc = upload(h, h->q_curfoot, cur_foot, B * 12);
+    if (rc) return rc;
+    if (!h->q_planner_set) {  // planner_foot_loc starts at the current foot locations in the body frame (ControllerParams.jl:62-66)
+        CK(h, cudaMemcpyAsync(h->q_planner, h->q_curfoot, B * 12 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        h->q_planner_set = true;
+    }
+    CK(h, quadruped_gait_launch((int)B, (int)K, h->q_t, h->q_xref, x_ref_per_knot, h->q_curfoot, g, h->dt, h->q_planner,
+                                h->q_contacts, h->q_foot, h->stream));
+    CK(h, quadruped_linearize_launch((int)B, (int)K, h->q_xref, x_ref_per_knot, nullptr, 0, h->q_foot, h->q_contacts, body,
+                                     h->dt, h->A, h->Bm, h->d, h->stream));
+    return ALTRO_OK;
+}
+
+int altro_quadruped_get_schedule(altro_handle_t h, double *contacts, double *foot)
+{
+    REQ(h);
+    if (!h->q_foot) return fail(h, ALTRO_ERR_STATE, "no quadruped schedule on the device yet");
+    const size_t cnt = (size_t)h->B * (h->N - 1);
+    int rc = ALTRO_OK;
+    if (contacts) rc = download(h, contacts, h->q_contacts, cnt * 4 * sizeof(double));
+    if (!rc && foot) rc = download(h, foot, h->q_foot, cnt * 12 * sizeof(double));
+    if (!rc) CK(h, cudaStreamSynchronize(h->stream));
+    return rc;
+}
+
+int altro_get_dynamics(altro_handle_t h, double *A, double *Bm, double *d)
+{
+    REQ(h);
+    if (!h->have_dyn) return fail(h, ALTRO_ERR_STATE, "dynamics not set");
+    const size_t n = h->n, m = h->m;
+    int rc = ALTRO_OK;
+    if (A) rc = download(h, A, h->A, h->dyn_count * n * n * sizeof(double));
+    if (!rc && Bm) rc = download(h, Bm, h->Bm, h->dyn_count * n * m * sizeof(double));
+    if (!rc && d) rc = download(h, d, h->d, h->dyn_count * n * sizeof(double));
+    if (!rc) CK(h, cudaStreamSynchronize(h->stream));
+    return rc;
 }
 
 int altro_host_register(void *ptr, size_t bytes)

@@ -1469,8 +1469,8 @@ struct Ctx {
         double *cs = reinterpret_cast<double *>(smem_base) + P.lay.cand + (warp > 0 ? (warp - 1) * set : 0);
         Ctx<NX, NU, 32> v(P, smem_base);
         v.tid = lane;
-        v.kcur = kcur;
-        v.sched = sched;
+        // the view works on THIS context's instance (persistent CTAs are re-bound, see bind()), not on blockIdx's
+        v.inst = inst; v.dyn_base = dyn_base; v.kcur = kcur; v.sched = sched; v.xr = xr; v.ur = ur; v.ex = ex;
         if (warp > 0) { v.Xb = cs; v.Ub = cs + N * n; v.itm = cs + N * n + (N - 1) * m; }
         else { v.Xb = Xb0; v.Ub = Ub0; v.itm = itm0; }
         double J = INFINITY, alpha = 1.0, z = -1.0;

@@ -137,3 +137,96 @@ def advance(prob: Problem, state: dict, rng: np.random.Generator, update_dt: flo
     A, Bm, d = linearized_dynamics(contact_schedule(state["t0"], prob.N), state["foot_rel"])
     prob.set_dynamics(A, Bm, d)
     prob.set_initial_state(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# numpy restatement of the quadruped's pre-solve step (checker of the device kernels in csrc/quadruped.cu)
+
+FOOT_RADIUS = 0.02  # Woofer.yaml:19
+GAIT_ALPHA = 0.5    # GaitParams.jl:33
+
+
+def mrp_rotation(p):
+    """Rotation matrix (body -> world) of a modified Rodrigues parameter vector, Rotations.MRP."""
+    p = np.asarray(p)
+    n2 = p @ p
+    S = np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]], dtype=p.dtype)
+    return np.eye(3, dtype=p.dtype) + (8.0 * (S @ S) + 4.0 * (1.0 - n2) * S) / (1.0 + n2) ** 2
+
+
+def nonlinear_dynamics(x, u, r, contacts, J=J_BODY, mass=MASS):
+    """NonLinearContinuousDynamics, linearized_dynamics.jl:1-36 (works on complex arguments: complex-step derivative)."""
+    x, u = np.asarray(x), np.asarray(u)
+    R = mrp_rotation(x[3:6])
+    p, ph, v, w = x[0:3], x[3:6], x[6:9], x[9:12]
+    kin = 0.25 * ((1.0 - ph @ ph) * w + 2.0 * np.cross(ph, w) + 2.0 * (ph @ w) * ph)  # Rotations.kinematics(MRP, w)
+    fs = np.array([0.0, 0.0, -9.81], dtype=x.dtype if np.iscomplexobj(x) else u.dtype)
+    ts = np.zeros(3, dtype=fs.dtype)
+    for i in range(4):
+        ui = u[3 * i:3 * i + 3]
+        fs = fs + contacts[i] / mass * ui
+        rb = R.T @ (r[i] - p)
+        ts = ts + contacts[i] * np.cross(rb, R.T @ ui)
+    wd = np.linalg.inv(J) @ (-np.cross(w, J @ w) + ts)
+    return np.concatenate([v, kin, fs, wd])
+
+
+def linearize_reference(x_ref, u_ref, foot, contacts, dt=DT, J=J_BODY, mass=MASS):
+    """update_dynamics_matrices!, altro_solver.jl:5-42, for one knot: Jacobians by the complex-step derivative (exact to
+    roundoff for this rational function; the reference uses ForwardDiff)."""
+    x_ref, u_ref = np.asarray(x_ref, float), np.asarray(u_ref, float)
+    h = 1e-30
+    Ac, Bc = np.zeros((12, 12)), np.zeros((12, 12))
+    for j in range(12):
+        xz = x_ref.astype(complex)
+        xz[j] += 1j * h
+        Ac[:, j] = nonlinear_dynamics(xz, u_ref.astype(complex), foot, contacts, J, mass).imag / h
+        uz = u_ref.astype(complex)
+        uz[j] += 1j * h
+        Bc[:, j] = nonlinear_dynamics(x_ref.astype(complex), uz, foot, contacts, J, mass).imag / h
+    dc = nonlinear_dynamics(x_ref, u_ref, foot, contacts, J, mass) - Ac @ x_ref - Bc @ u_ref
+    return np.eye(12) + Ac * dt, Bc * dt, dc * dt
+
+
+def foot_history_reference(t, x_ref, cur_foot, planner, K, dt=DT, contact_phases=None, phase_times=PHASE_T,
+                           nom_foot=NOM_FOOT, alpha=GAIT_ALPHA, foot_radius=FOOT_RADIUS):
+    """foot_history! (footsteps.jl:29-84) + get_phase (gait.jl:1-9) + footstep_location (footsteps.jl:1-27) of one
+    instance.  x_ref (12,) or (K,12); cur_foot (4,3) body frame; planner (4,3) in/out.  Returns contacts (K,4),
+    foot (K,4,3) world and the updated planner state."""
+    cp = TROT.T if contact_phases is None else np.asarray(contact_phases, float)  # (num_phases, 4)
+    x_ref = np.asarray(x_ref, float)
+    xr = (lambda k: x_ref[k]) if x_ref.ndim == 2 else (lambda k: x_ref)
+    total = float(np.sum(phase_times))
+
+    def phase_of(tt):
+        pt, s = np.fmod(tt, total), 0.0
+        for i, d in enumerate(phase_times):
+            s += d
+            if pt < s:
+                return i
+        return len(phase_times) - 1
+
+    planner = np.array(planner, float)
+    contacts, foot = np.zeros((K, 4)), np.zeros((K, 4, 3))
+    prev_phase = phase_of(t)
+    x = xr(0)
+    prev = x[0:3] + (mrp_rotation(x[3:6]) @ np.asarray(cur_foot, float).T).T
+    contacts[0], foot[0] = cp[prev_phase], prev
+    t_i = t + dt
+    for k in range(1, K):
+        nxt = phase_of(t_i)
+        x = xr(k)
+        R = mrp_rotation(x[3:6])
+        contacts[k] = cp[nxt]
+        for j in range(4):
+            if cp[prev_phase][j] == 1:
+                if cp[nxt][j] == 0:
+                    t_next = phase_times[(nxt + 1) % len(phase_times)]
+                    loc = x[0:3] + R @ nom_foot[j] + alpha * t_next * x[6:9]
+                    planner[j] = np.array([loc[0], loc[1], foot_radius])
+            elif cp[nxt][j] == 1:
+                prev[j] = planner[j]
+        foot[k] = prev
+        t_i += dt
+        prev_phase = nxt
+    return contacts, foot, planner

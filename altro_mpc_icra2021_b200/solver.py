@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "altro_host_register", "altro_host_unregister", "altro_set_launch_config", "altro_get_launch_info",
     "altro_set_line_search_mode", "altro_get_line_search_mode", "altro_reserve_steps",
     "altro_set_kernel_mode", "altro_get_kernel_mode", "altro_set_run_queue",
+    "altro_admm_solve", "altro_quadruped_linearize", "altro_quadruped_tick", "altro_quadruped_get_schedule", "altro_get_dynamics",
     "altro_measure_peaks",
 ]
 
@@ -381,6 +382,63 @@ class ALTROSolver:
         out = np.zeros((self.prob.B, 8), np.int64)
         self._ck(self.lib.altro_get_phase_cycles(self.h, int(enable), _p(out)))
         return out
+
+    # ------------------------------------------------------------------ independent convex cross-check
+    def admm_solve(self, rho: float = 10.0, eps: float = 1e-6, max_iter: int = 4000) -> dict:
+        """Solves the current problems with the batched operator-splitting solver (csrc/admm.cu), the stand-in for the
+        reference's OSQP / ECOS cross-check.  Does not touch the solver's own trajectories."""
+        p, B = self.prob, self.prob.B
+        self.upload()
+        X, U = np.zeros((B, p.N, p.n)), np.zeros((B, p.N - 1, p.m))
+        it, rp, rd = np.zeros(B, np.int32), np.zeros(B), np.zeros(B)
+        self._ck(self.lib.altro_admm_solve(self.h, C.c_double(rho), C.c_double(eps), int(max_iter), _p(X), _p(U), _p(it),
+                                           _p(rp), _p(rd)))
+        return {"X": X, "U": U, "iterations": it, "r_prim": rp, "r_dual": rd}
+
+    # ------------------------------------------------------------------ quadruped pre-solve kernels
+    def quadruped_linearize(self, x_ref, foot, contacts, J, mass, u_ref=None) -> None:
+        """update_dynamics_matrices! (altro_solver.jl:5-42) on the device: writes A_k, B_k, d_k of every instance and
+        knot into the solver's model.  x_ref (B,12) or (B,N-1,12); foot (B,N-1,4,3) world; contacts (B,N-1,4)."""
+        x = np.ascontiguousarray(x_ref, dtype=np.float64)
+        u = None if u_ref is None else np.ascontiguousarray(u_ref, dtype=np.float64)
+        f, c = np.ascontiguousarray(foot, dtype=np.float64), np.ascontiguousarray(contacts, dtype=np.float64)
+        Jm = np.ascontiguousarray(J, dtype=np.float64)
+        self.upload()
+        self._ck(self.lib.altro_quadruped_linearize(self.h, _p(x), int(x.ndim == 3), _p(u), int(u is not None and u.ndim == 3),
+                                                    _p(f), _p(c), _p(Jm), C.c_double(mass)))
+        self.prob.dirty["dyn"] = False
+        self._ck(self.lib.altro_sync(self.h))
+
+    def quadruped_tick(self, t, x_ref, cur_foot, contact_phases, phase_times, nom_foot, J, mass, alpha=0.5,
+                       foot_radius=0.02) -> None:
+        """foot_history! + update_dynamics_matrices! of one control tick on the device (footsteps.jl:29-84,
+        altro_solver.jl:5-42).  t (B,), x_ref (B,12) or (B,N-1,12), cur_foot (B,4,3) body frame,
+        contact_phases (num_phases,4), phase_times (num_phases,)."""
+        tt = np.ascontiguousarray(t, dtype=np.float64)
+        x = np.ascontiguousarray(x_ref, dtype=np.float64)
+        cf = np.ascontiguousarray(cur_foot, dtype=np.float64)
+        cp = np.ascontiguousarray(contact_phases, dtype=np.float64)
+        pt = np.ascontiguousarray(phase_times, dtype=np.float64)
+        nf, Jm = np.ascontiguousarray(nom_foot, dtype=np.float64), np.ascontiguousarray(J, dtype=np.float64)
+        self.upload()
+        self._ck(self.lib.altro_quadruped_tick(self.h, _p(tt), _p(x), int(x.ndim == 3), _p(cf), int(cp.shape[0]), _p(cp),
+                                               _p(pt), C.c_double(alpha), C.c_double(foot_radius), _p(nf), _p(Jm),
+                                               C.c_double(mass)))
+        self.prob.dirty["dyn"] = False
+        self._ck(self.lib.altro_sync(self.h))
+
+    def quadruped_schedule(self):
+        B, K = self.prob.B, self.prob.N - 1
+        c, f = np.zeros((B, K, 4)), np.zeros((B, K, 4, 3))
+        self._ck(self.lib.altro_quadruped_get_schedule(self.h, _p(c), _p(f)))
+        return c, f
+
+    def get_dynamics(self):
+        """The model as it is on the device (A, B, d in the layout of prob.model)."""
+        mdl = self.prob.model
+        A, Bm, d = np.zeros_like(mdl.A), np.zeros_like(mdl.B), np.zeros_like(mdl.d)
+        self._ck(self.lib.altro_get_dynamics(self.h, _p(A), _p(Bm), _p(d)))
+        return A, Bm, d
 
     def set_run_queue(self, steps_per_item: int) -> None:
         """Scheduling of mpc_run: >= 1 = persistent grid + work queue of (instance, steps_per_item steps) items

@@ -193,6 +193,39 @@ int altro_get_run_results(altro_handle_t h, int steps, int *iterations, int *ite
                           int *ls_trials, double *cost, double *c_max, double *x0_log, double *u0_log,
                           long long *t_ns);
 
+/* Independent convex cross-check on the device: the reference validates every ALTRO solve against
+ * OSQP / ECOS / COSMO / Mosek (random_linear_problem.jl:37-77,141-186, simple_rocket.jl:184-192, grasp_mpc.jl:75-80).
+ * altro_admm_solve solves the handle's CURRENT problems (x0, reference, dynamics, constraint blocks as the next
+ * altro_solve would see them) with a batched operator-splitting solver that shares no code path with the AL-iLQR
+ * kernels (csrc/admm.cu): fixed penalty rho, stops when the primal and dual residuals are below eps or after
+ * max_iter iterations.  The handle's own trajectories and duals are not touched.  X[B][N][n], U[B][N-1][m],
+ * per-instance iterations and final residuals; any output may be NULL. */
+int altro_admm_solve(altro_handle_t h, double rho, double eps, int max_iter, double *X, double *U, int *iterations,
+                     double *r_prim, double *r_dual);
+
+/* Quadruped, the step before the solve path, on the device.
+ * altro_quadruped_linearize replaces update_dynamics_matrices! (altro_solver.jl:5-42): A_k = I + A_c dt, B_k = B_c dt,
+ * d_k = (f - A_c x_ref - B_c u_ref) dt with A_c, B_c the Jacobians of NonLinearContinuousDynamics
+ * (linearized_dynamics.jl:1-66, forward-mode AD like the reference's ForwardDiff) at x_ref[B][(N-1)?][12],
+ * u_ref[B][(N-1)?][12] (NULL = 0), world foot positions foot[B][N-1][4][3], contact flags contacts[B][N-1][4],
+ * body inertia J[3][3] and sprung mass.  The result is written into the handle's per-instance, per-knot model
+ * (opt.model.A[i] = ..., altro_solver.jl:35-37) without passing through the host.
+ * altro_quadruped_tick additionally builds the contact pattern and the foot positions of the horizon on the device
+ * from the tick time t[B] and the current body-frame foot positions cur_foot[B][4][3]: foot_history! (footsteps.jl:29-84)
+ * with get_phase (gait.jl:1-9) and footstep_location (footsteps.jl:1-27); contact_phases[num_phases][4],
+ * phase_times[num_phases], alpha / foot_radius / nom_foot[4][3] as in GaitParams.jl:38-49, Woofer.yaml.  The footstep
+ * planner's state (planner_foot_loc) lives in the handle.  altro_quadruped_get_schedule / altro_get_dynamics read the
+ * results back (tests, logging). */
+int altro_quadruped_linearize(altro_handle_t h, const double *x_ref, int x_ref_per_knot, const double *u_ref,
+                              int u_ref_per_knot, const double *foot, const double *contacts, const double *J,
+                              double mass);
+int altro_quadruped_tick(altro_handle_t h, const double *t, const double *x_ref, int x_ref_per_knot,
+                         const double *cur_foot, int num_phases, const double *contact_phases,
+                         const double *phase_times, double alpha, double foot_radius, const double *nom_foot,
+                         const double *J, double mass);
+int altro_quadruped_get_schedule(altro_handle_t h, double *contacts, double *foot);
+int altro_get_dynamics(altro_handle_t h, double *A, double *B, double *d);
+
 /* Pin / unpin a caller buffer so setters and getters DMA directly (cudaHostRegister). */
 int altro_host_register(void *ptr, size_t bytes);
 int altro_host_unregister(void *ptr);

@@ -131,13 +131,15 @@ def test_lane_kernel_matches_oracle_and_cta_kernel(batch):
 def test_lane_kernel_is_opt_in_and_limited_to_small_shared_lti_problems():
     cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
     prob, opts, _, _ = cases.case_rocket_mpc(cold["X"], cold["U"], batch=64)
+    p2 = copy.deepcopy(prob)  # (a solver consumes the problem's dirty flags: one problem object per solver)
     assert gpu_solver(prob, opts).launch_info()["kernel"] == "cta"
-    assert gpu_solver(copy.deepcopy(prob), opts, kernel="lane").launch_info()["kernel"] == "lane"
+    assert gpu_solver(p2, opts, kernel="lane").launch_info()["kernel"] == "lane"
     pq, oq, _, _ = cases.case_quadruped(True, batch=4)
+    pq2 = copy.deepcopy(pq)
     assert gpu_solver(pq, oq).launch_info()["kernel"] == "cta"
     from altro_mpc_icra2021_b200.solver import AltroError
-    with pytest.raises(AltroError):
-        gpu_solver(copy.deepcopy(pq), oq, kernel="lane").solve()
+    with pytest.raises(AltroError, match="lane-per-instance"):
+        gpu_solver(pq2, oq, kernel="lane").solve()
 
 
 def test_speculative_line_search_on_long_horizon_family():
