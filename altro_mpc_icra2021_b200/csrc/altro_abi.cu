@@ -285,6 +285,7 @@ const void *kernel_6_6(int T);    // grasp
 const void *kernel_12_3(int T);   // flexible satellite
 const void *kernel_12_6(int T);   // random linear (default)
 const void *kernel_0_0(int T);    // run-time dimensions
+const void *kernel_0_0_wide(int T);  // run-time dimensions, one CTA per SM (TMA-staged large-dimension layout)
 bool lane_supported(int n, int m);  // lane-per-instance kernels (6, 3), (6, 6)
 cudaError_t lane_launch(int n, int m, const LaneLaunch &a);
 }  // namespace altro
@@ -446,10 +447,15 @@ int finalize(altro_handle_t h)
     if ((size_t)h->lay.bytes > limit || (big_env ? atoi(big_env) != 0 : lonely)) {
         // Large state dimension: n-sized matrices and gains in a per-instance global workspace (make_layout_big).
         if (h->ex_glob == nullptr && EX > 0) CK(h, dalloc(&h->ex_glob, (size_t)B * EX));
-        Layout lb = make_layout_big(n, m, N, P, ncons, 0);
+        // TMA-staged operand panels (Ctx::panel_gemm): bit-identical, but measured SLOWER than the register-blocked tiles
+        // fed from L2 (profiles/r2_large_n.md: 877-992 vs 1383 solves/s at n = 200), so opt-in: ALTRO_B200_TMA=1
+        int want_tma = 0;
+        if (const char *e = getenv("ALTRO_B200_TMA")) want_tma = (T == 256 && atoi(e)) ? 1 : 0;
+        Layout lb = make_layout_big(n, m, N, P, ncons, 0, want_tma);
+        if ((size_t)lb.bytes > limit && lb.tma) lb = make_layout_big(n, m, N, P, ncons, 0, 0);  // no room for the panel stages
         if ((size_t)lb.bytes <= limit) {
             h->lay = lb;
-            h->kernel = kernel_0_0(T);
+            h->kernel = (lb.tma && kernel_0_0_wide(T)) ? kernel_0_0_wide(T) : kernel_0_0(T);
             h->ref_in_smem = 0;
             h->dyn_in_smem = 0;
             h->spec = 0;

@@ -50,6 +50,7 @@ struct Layout {
         t1, linv, red, bc, itm, cand, Qi, cd;  // cd: offset (in doubles) of the ConDesc array, followed by the gather tables
     int bytes;                       // total dynamic shared memory
     int big, ws_doubles;             // large state dimension: the n-sized matrices live in a global workspace (offsets into it)
+    int tma, stage, stage_doubles, mbar;  // large state dimension: TMA-staged operand panels (see Ctx::panel_gemm)
 };
 
 #ifndef ALTRO_T128_CTAS
@@ -83,7 +84,13 @@ __host__ __device__ constexpr Layout fixed_layout(int n, int m)
 // side -- S, SA, Qxx, SB, Qux, T1, the gains K and the gathered expansion Qi -- move to a per-instance workspace in
 // global memory (L2-resident), the dynamics are read in place, the gather tables stay in global memory; vectors,
 // trajectories, duals, the m x m blocks and the descriptors stay in shared memory.  Same code, other pointers.
-__host__ __device__ inline Layout make_layout_big(int n, int m, int N, int P, int ncon, int EX)
+// shared-memory row stride of a staged panel: rows whose length is a multiple of 8 doubles are padded by 4 so that the
+// four k-rows a DMMA fragment load touches fall into different banks (stride = 4 mod 8 doubles)
+__host__ __device__ constexpr int panel_ld(int ld) { return (ld % 8 == 0) ? ld + 4 : ld; }
+constexpr int PANEL_KC = 8;   // k-rows per staged operand panel
+constexpr int PANEL_NST = 3;  // stages in flight
+
+__host__ __device__ inline Layout make_layout_big(int n, int m, int N, int P, int ncon, int EX, int tma = 1)
 {
     Layout l{};
     int q = 0, w = 0;
@@ -98,10 +105,19 @@ __host__ __device__ inline Layout make_layout_big(int n, int m, int N, int P, in
     l.dv = take((N - 1) * m); l.lam = take(P); l.ex = take(EX); l.itm = take(N * (1 + ncon));
     l.cand = q;
     q += q & 1;
+    // TMA-staged panels: rows must be 16-byte multiples and K a multiple of 4 (n % 4 == 0); each stage holds
+    // PANEL_KC k-rows of both operands (+ 32 doubles of slack each: partial edge tiles read past the row end)
+    l.tma = (tma && n % 4 == 0 && n >= 32) ? 1 : 0;
+    if (l.tma) {
+        l.stage_doubles = PANEL_KC * (panel_ld(n) + panel_ld(n > m ? n : m)) + 64;
+        l.stage = take(PANEL_NST * l.stage_doubles);
+        l.mbar = take(2 * PANEL_NST);
+    }
     l.cd = q;
     l.sA = l.sB = 0;  // unused: A_k, B_k are read where they are
     l.S = wtake(n * n); l.SA = wtake(n * n); l.Qxx = wtake(n * n); l.SB = wtake(n * m); l.Qux = wtake(m * n);
     l.T1 = wtake(m * n); l.Qi = wtake(n + n * n + m + m * m); l.K = wtake((N - 1) * m * n);
+    w += w & 1;  // instances start on 16-byte boundaries (bulk copies)
     size_t b = (size_t)q * sizeof(double) + (size_t)(ncon > 0 ? ncon : 1) * sizeof(ConDesc);
     l.bytes = (int)((b + 15) & ~(size_t)15);
     l.big = 1;
@@ -292,8 +308,40 @@ __device__ __noinline__ bool ldl_solve_medium(double *L, double *linv, const dou
     return false;
 }
 
+// ---- TMA bulk copies and mbarriers (sm_90+ PTX): operand panels of the large-dimension GEMMs are fetched by the copy
+// engine into shared memory while the warps run tensor tiles on the previous panel.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // Per-instance context: shared-memory pointers and problem view.
-template <int NX, int NU, int T>
+// WIDE: the variant compiled into altro_solve_kernel_wide (whole register file, TMA-staged panels); the default kernels
+// do not carry that code.
+template <int NX, int NU, int T, bool WIDE = false>
 struct Ctx {
     static constexpr bool ALL_SMEM = NX > 0 && NU > 0 && ALTRO_FIXED_ALL_SMEM;
     const Params &P;
@@ -314,6 +362,7 @@ struct Ctx {
     int dyn_k;
     const int *sched;  // this instance's dynamics schedule at the current MPC step, or nullptr
     int kcur;          // this instance's position on the shared timelines (reference track, track constraints)
+    unsigned pg_count = 0;  // operand panels streamed so far (stage and mbarrier phase follow from it; same in every thread)
 
     __device__ Ctx(const Params &P_, unsigned char *raw) : P(P_), smem_base(raw)
     {
@@ -415,6 +464,13 @@ struct Ctx {
     // Hessian entries no block touches.
     __device__ void load_static()
     {
+        if constexpr (WIDE) {
+            if (P.lay.big && P.lay.tma && tid == 0) {  // panel pipeline barriers (panel_gemm)
+                uint64_t *mb = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_base) + P.lay.mbar);
+                for (int i = 0; i < PANEL_NST; ++i) { mbar_init(mb + i, 1); mbar_init(mb + PANEL_NST + i, T / 32); }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+        }
 #pragma unroll 1
         for (int i = tid; i < n; i += T) { Qd[i] = P.Q[i]; Qfd[i] = P.Qf[i]; }
 #pragma unroll 1
@@ -962,6 +1018,102 @@ struct Ctx {
         }
     }
 
+    // ---- TMA-staged panel GEMM (large state dimension):  C(i,j) = init(i,j) + sum_l PA[l][i] PB[l][j],  l ascending.
+    // Both operands are "k-major" (row l of PA holds column l of the left factor), so a panel of PANEL_KC k-rows of
+    // each is ONE contiguous block in global memory and goes to shared memory with one cp.async.bulk per operand,
+    // PANEL_NST panels in flight behind mbarriers (full: transaction bytes; empty: one arrival per warp).  A warp owns a
+    // 32 x 32 block of C (4 x 4 DMMA tiles, 16 independent accumulator chains per k-step fed by 8 shared-memory
+    // fragment loads); the blocks of a round (one per warp) share every panel.  Each element's chain is the same
+    // sequence of mma.sync.m8n8k4 steps over ascending l as in tile_gemm, so the bits do not change.
+    // S A uses PA = S: S is symmetric to the last bit (it is formed as (D + D')/2 with commutative operations).
+    template <class FI, class FS>
+    __device__ __forceinline__ void panel_gemm(int M, int Nc, int K, const double *PA, int lda, const double *PB, int ldb,
+                                               FI init, FS store)
+    {
+        constexpr int NW = T / 32;
+        const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
+        double *stage0 = reinterpret_cast<double *>(smem_base) + P.lay.stage;
+        uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_base) + P.lay.mbar), *empty = full + PANEL_NST;
+        const int lsa = panel_ld(lda), lsb = panel_ld(ldb);  // row strides in shared memory
+        const int sd = P.lay.stage_doubles, boff = PANEL_KC * lsa + 32;
+        const int nbc = (Nc + 31) >> 5, nblk = ((M + 31) >> 5) * nbc, rounds = (nblk + NW - 1) / NW;
+        const int nchunk = (K + PANEL_KC - 1) / PANEL_KC, total = rounds * nchunk;
+        auto issue = [&](int g) {  // thread 0: panel g of this call into its stage
+            const unsigned G = pg_count + g, st = G % PANEL_NST, use = G / PANEL_NST;
+            if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
+            const int c = g % nchunk, rows = min(PANEL_KC, K - c * PANEL_KC);
+            double *As = stage0 + st * sd, *Bs = As + boff;
+            const uint32_t ba = (uint32_t)(rows * lda * sizeof(double)), bb = (uint32_t)(rows * ldb * sizeof(double));
+            mbar_expect_tx(full + st, ba + bb);
+            if (lsa == lda) bulk_g2s(As, PA + (size_t)c * PANEL_KC * lda, ba, full + st);
+            else
+                for (int rr = 0; rr < rows; ++rr)
+                    bulk_g2s(As + rr * lsa, PA + ((size_t)c * PANEL_KC + rr) * lda, (uint32_t)(lda * sizeof(double)), full + st);
+            if (lsb == ldb) bulk_g2s(Bs, PB + (size_t)c * PANEL_KC * ldb, bb, full + st);
+            else
+                for (int rr = 0; rr < rows; ++rr)
+                    bulk_g2s(Bs + rr * lsb, PB + ((size_t)c * PANEL_KC + rr) * ldb, (uint32_t)(ldb * sizeof(double)), full + st);
+        };
+        if (tid == 0)
+            for (int g = 0; g < PANEL_NST - 1 && g < total; ++g) issue(g);
+        double acc[4][4][2];
+        int i0 = 0, j0 = 0;
+        bool active = false;
+#pragma unroll 1
+        for (int g = 0; g < total; ++g) {
+            if (tid == 0 && g + PANEL_NST - 1 < total) issue(g + PANEL_NST - 1);
+            const int c = g % nchunk;
+            if (c == 0) {
+                const int b = (g / nchunk) * NW + warp;
+                active = b < nblk;
+                i0 = (b / nbc) << 5;
+                j0 = (b - (b / nbc) * nbc) << 5;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        acc[x][y][0] = active ? init(i0 + 8 * x + r, j0 + 8 * y + 2 * q) : 0.0;
+                        acc[x][y][1] = active ? init(i0 + 8 * x + r, j0 + 8 * y + 2 * q + 1) : 0.0;
+                    }
+            }
+            const unsigned G = pg_count + g, st = G % PANEL_NST, use = G / PANEL_NST;
+            mbar_wait(full + st, use & 1);
+            if (active) {
+                const double *As = stage0 + st * sd, *Bs = As + boff;
+                const int steps = min(PANEL_KC, K - c * PANEL_KC) >> 2;
+#pragma unroll 2
+                for (int kk = 0; kk < steps; ++kk) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) a[x] = As[(kk * 4 + q) * lsa + i0 + 8 * x + r];
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) b[y] = Bs[(kk * 4 + q) * lsb + j0 + 8 * y + r];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(acc[x][y][0]), "+d"(acc[x][y][1]) : "d"(a[x]), "d"(b[y]));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + st);
+            if (c == nchunk - 1 && active) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        store(i0 + 8 * x + r, j0 + 8 * y + 2 * q, acc[x][y][0]);
+                        store(i0 + 8 * x + r, j0 + 8 * y + 2 * q + 1, acc[x][y][1]);
+                    }
+            }
+        }
+        pg_count += total;
+        // the results go to global memory through the generic proxy and are the next product's operands (async proxy)
+        fence_proxy_async();
+        __syncthreads();
+    }
+
     // Returns false if Quu could not be made positive definite.
     __device__ bool backward_pass(double &rho, double &drho, double &dV1, double &dV2)
     {
@@ -1008,7 +1160,17 @@ struct Ctx {
                 const bool big = MAYBE_BIG && P.lay.big;
                 auto zero_a = [](int, int) { return 0.0; };
                 // P1: SA = S A, SB = S B (tensor tiles); A_k, B_k and Qi were prepared during the previous knot
-                if (big) {
+                const bool tma = WIDE && big && P.lay.tma;
+                if (tma) {
+                    if constexpr (WIDE) {
+                        fence_proxy_async();  // S (and the first knot's terminal S) was written with ordinary stores
+                        __syncthreads();
+                        panel_gemm(n, n, n, S, n, A, n, [](int, int) { return 0.0; },
+                                   [&](int i, int j, double v) { if (i < n && j < n) SA[i * n + j] = v; });
+                        panel_gemm(n, m, n, S, n, Bm, m, [](int, int) { return 0.0; },
+                                   [&](int i, int j, double v) { if (i < n && j < m) SB[i * m + j] = v; });
+                    }
+                } else if (big) {
                     tile_gemm(n, n, [](int, int) { return 0.0; }, n,
                               [&](int i, int l) { return (i < n && l < n) ? S[i * n + l] : 0.0; },
                               [&](int l, int j) { return (l < n && j < n) ? A[l * n + j] : 0.0; }, 0, zero_a, zero_a,
@@ -1047,7 +1209,33 @@ struct Ctx {
                 // P2: [Qxx | Qx] += A'[SA | s],  Qux = B'SA,  [Quu | Qu] += B'[SB | s]   (chains start from the
                 //     cost + AL expansion already in Qxx / Qx / Quu / Qu)
                 const int nt_xx = tn * tn1, nt_ux = tm * tn, nt_uu = tm * tm1;
-                if (big) {
+                if (tma) {
+                    if constexpr (WIDE) {
+                        panel_gemm(n, n, n, A, n, SA, n,
+                                   [&](int i, int j) { return (i < n && j < n) ? Qi[oQxx + i * n + j] : 0.0; },
+                                   [&](int i, int j, double v) { if (i < n && j < n) Qxx[i * n + j] = v; });
+                        panel_gemm(m, n, n, Bm, m, SA, n, [](int, int) { return 0.0; },
+                                   [&](int i, int j, double v) { if (i < m && j < n) Qux[i * n + j] = v; });
+                        panel_gemm(m, m, n, Bm, m, SB, m,
+                                   [&](int i, int j) { return (i < m && j < m) ? Qi[oQuu + i * m + j] : 0.0; },
+                                   [&](int i, int j, double v) {
+                                       if (i < m && j < m) { Quu[i * m + j] = v; L[i * m + j] = v + ((i == j) ? rho : 0.0); }
+                                   });
+                        // the vector columns of the two tiles: Qx = Qi + A's, Qu = Qi + B's (same chains, one thread each)
+                        for (int i = tid; i < n + m; i += T) {
+                            if (i < n) {
+                                double acc = Qi[i];
+                                for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], s[l], acc);
+                                Qx[i] = acc;
+                            } else {
+                                const int iu = i - n;
+                                double acc = Qi[oQu + iu];
+                                for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + iu], s[l], acc);
+                                Qu[iu] = acc;
+                            }
+                        }
+                    }
+                } else if (big) {
                     tile_gemm(n, n + 1,
                               [&](int i, int j) { return i < n ? (j < n ? Qi[oQxx + i * n + j] : (j == n ? Qi[i] : 0.0)) : 0.0; }, n,
                               [&](int i, int l) { return (i < n && l < n) ? A[l * n + i] : 0.0; },
@@ -1802,6 +1990,17 @@ __global__ void __launch_bounds__(T, ((NX == 12 && NU == 12) ? (256 / T > 0 ? 25
     if constexpr (T > 32) {
         if (P.q_head) { ctx.solve_queued(); return; }
     }
+    ctx.solve();
+}
+
+// The same run-time sized solve with the whole register file (one CTA per SM): the TMA-staged large-dimension layout is
+// shared-memory-limited to one CTA per SM anyway, and its 32 x 32 register blocks want the registers.
+template <int T>
+__global__ void __launch_bounds__(T, 1) altro_solve_kernel_wide(const __grid_constant__ Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx<0, 0, T, true> ctx(P, smem_raw);
+    if (P.q_head) { ctx.solve_queued(); return; }
     ctx.solve();
 }
 
