@@ -183,7 +183,7 @@ struct Params {
     Layout lay;
     int spec;  // line-search trials evaluated concurrently, one per warp (0 = sequential)
     // closed-loop runs on a persistent grid: work items (instance, chunk of `q_chunk` steps) are handed out chunk-major
-    // from q_head; q_done[inst] = number of steps of the instance that are complete and stored (see Ctx::solve_queued)
+    // from q_head; q_done[inst] = number of steps of the instance that are complete and stored (see Ctx::solve)
     int q_chunk;
     int *q_head, *q_done, *q_error;
     altro_opts_t o;
@@ -1798,7 +1798,7 @@ struct Ctx {
     }
 
     // ---------------------------------------------------------------- solve! (A.4 - A.6)
-    __device__ void solve_core(int slot)
+    __device__ __forceinline__ void solve_core(int slot)
     {
         const altro_opts_t &o = P.o;
         long long ph[4] = {0, 0, 0, 0};
@@ -1885,7 +1885,7 @@ struct Ctx {
     }
 
     // steps [s0, s1) of the closed-loop run of the bound instance (or the one plain solve! when P.steps == 0)
-    __device__ void run_steps(int s0, int s1, long long t0)
+    __device__ __forceinline__ void run_steps(int s0, int s1, long long t0)
     {
 #pragma unroll 1
         for (int st = s0; st < s1; ++st) {
@@ -1918,61 +1918,69 @@ struct Ctx {
         }
     }
 
-    __device__ void solve()
+    // One plain solve! / one closed-loop run of the CTA's own instance (P.q_head == nullptr), or the closed-loop run on a
+    // persistent grid (one CTA per resident slot): the CTAs pull (instance, chunk of q_chunk steps) items from an atomic
+    // counter, chunk-major, so that every slot stays busy until the whole batch is done -- no wave quantisation (4096
+    // instances over 1184 slots = 3.46 waves) and no waiting for the slot that happened to get the longest chains.  An
+    // item needs the instance's previous chunk: it was handed out a whole round (B items) earlier, so it is normally
+    // long finished; otherwise thread 0 waits on q_done[inst].  State travels through global memory (a few KB per item,
+    // L2-resident), written with a release fence and read through L2.
+    // Both modes share ONE call site of run_steps(): with two, the compiler keeps solve_core() out of line and the whole
+    // Ctx moves to local memory (measured: 3.3x slower at T = 128).
+    __device__ __forceinline__ void solve()
     {
-        long long t0 = 0;
-        if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        load();
-        run_steps(0, P.steps > 0 ? P.steps : 1, t0);
-        store();
-    }
-
-    // Closed-loop run on a persistent grid (one CTA per resident slot): the CTAs pull (instance, chunk of q_chunk
-    // steps) items from an atomic counter, chunk-major, so that every slot stays busy until the whole batch is done
-    // -- no wave quantisation (4096 instances over 1184 slots = 3.46 waves) and no waiting for the slot that happened
-    // to get the longest chains.  An item needs the instance's previous chunk: it was handed out a whole round (B
-    // items) earlier, so it is normally long finished; otherwise thread 0 waits on q_done[inst].  State travels
-    // through global memory (a few KB per item, L2-resident), written with a release fence and read through L2.
-    __device__ void solve_queued()
-    {
-        load_static();
-        gsync<T>();
-        const int chunk = P.q_chunk, nchunk = (P.steps + chunk - 1) / chunk;
-        const long long total = (long long)nchunk * P.B;
+        const bool queued = T > 32 && P.q_head != nullptr;
+        const int chunk = queued ? P.q_chunk : 0;
+        const long long total = queued ? (long long)((P.steps + chunk - 1) / chunk) * P.B : 0;
+        if (queued) {
+            load_static();
+            gsync<T>();
+        }
+#pragma unroll 1
         for (;;) {
-            if (tid == 0) {
-                const long long t = (long long)atomicAdd(P.q_head, 1);
-                int go = t < total ? 1 : 0;
-                if (go) {
-                    const int i = (int)(t % P.B), c = (int)(t / P.B);
-                    if (c > 0) {  // wait for the instance's previous chunk (bounded: a lost item must not hang the GPU)
-                        const long long w0 = clock64();
-                        while (atomicAdd(P.q_done + i, 0) < c * chunk) {
-                            __nanosleep(256);
-                            if (clock64() - w0 > (1ll << 33)) { atomicExch(P.q_error, 1); go = 0; break; }
+            int s0 = 0, s1 = P.steps > 0 ? P.steps : 1, item = inst;
+            if (queued) {
+                if (tid == 0) {
+                    const long long t = (long long)atomicAdd(P.q_head, 1);
+                    int go = t < total ? 1 : 0;
+                    if (go) {
+                        const int i = (int)(t % P.B), c = (int)(t / P.B);
+                        if (c > 0) {  // wait for the instance's previous chunk (bounded: a lost item must not hang the GPU)
+                            const long long w0 = clock64();
+                            while (atomicAdd(P.q_done + i, 0) < c * chunk) {
+                                __nanosleep(256);
+                                if (clock64() - w0 > (1ll << 33)) { atomicExch(P.q_error, 1); go = 0; break; }
+                            }
                         }
+                        reinterpret_cast<int *>(bc)[0] = i;
+                        reinterpret_cast<int *>(bc)[1] = c;
                     }
-                    reinterpret_cast<int *>(bc)[0] = i;
-                    reinterpret_cast<int *>(bc)[1] = c;
+                    reinterpret_cast<int *>(bc)[2] = go;
                 }
-                reinterpret_cast<int *>(bc)[2] = go;
+                __syncthreads();
+                const int go = reinterpret_cast<int *>(bc)[2], c = reinterpret_cast<int *>(bc)[1];
+                item = reinterpret_cast<int *>(bc)[0];
+                __syncthreads();
+                if (!go) break;
+                __threadfence();  // acquire: the previous chunk's rows are visible before they are read
+                s0 = c * chunk;
+                s1 = min(P.steps, s0 + chunk);
             }
-            __syncthreads();
-            const int go = reinterpret_cast<int *>(bc)[2], i = reinterpret_cast<int *>(bc)[0], c = reinterpret_cast<int *>(bc)[1];
-            __syncthreads();
-            if (!go) break;
-            __threadfence();  // acquire: the previous chunk's rows are visible before they are read
             long long t0 = 0;
             if (tid == 0 && P.t_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            bind(i);
-            load_state<true>();
-            gsync<T>();
-            const int s0 = c * chunk, s1 = min(P.steps, s0 + chunk);
+            if (queued) {
+                bind(item);
+                load_state<true>();
+                gsync<T>();
+            } else {
+                load();
+            }
             run_steps(s0, s1, t0);
             store();
+            if (!queued) break;
             __threadfence();  // release: rows first, then the step count
             __syncthreads();
-            if (tid == 0) atomicExch(P.q_done + i, s1);
+            if (tid == 0) atomicExch(P.q_done + item, s1);
         }
     }
 };
@@ -1987,9 +1995,6 @@ __global__ void __launch_bounds__(T, ((NX == 12 && NU == 12) ? (256 / T > 0 ? 25
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<NX, NU, T> ctx(P, smem_raw);
-    if constexpr (T > 32) {
-        if (P.q_head) { ctx.solve_queued(); return; }
-    }
     ctx.solve();
 }
 
@@ -2000,7 +2005,6 @@ __global__ void __launch_bounds__(T, 1) altro_solve_kernel_wide(const __grid_con
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<0, 0, T, true> ctx(P, smem_raw);
-    if (P.q_head) { ctx.solve_queued(); return; }
     ctx.solve();
 }
 

@@ -472,7 +472,7 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     headline = args.workload or os.environ.get("ALTRO_BENCH_WORKLOAD") or "rocket"
     if args.secondary is not None:
-        secondary = [w for w in args.secondary.split(",") if w]
+        secondary = [w for w in args.secondary.split(",") if w and w != "none"]
     else:
         secondary = ["quadruped"] if args.workload is None and "ALTRO_BENCH_WORKLOAD" not in os.environ else []
     base = {"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "higher_is_better": True,
