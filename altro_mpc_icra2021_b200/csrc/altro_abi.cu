@@ -996,7 +996,7 @@ static int launch_solve(altro_handle_t h, int steps, int shift)
     int chunk = h->run_chunk;
     if (const char *e = getenv("ALTRO_B200_QUEUE")) chunk = atoi(e);
     const bool lane = h->lane_kern && !h->trace && !h->phase;
-    const bool queued = steps > 0 && chunk > 0 && !lane && h->threads > 32 && !h->lay.big && !h->trace &&
+    const bool queued = steps > 0 && chunk > 0 && !lane && h->threads > 32 && !h->trace &&
                         (long long)h->B * ((steps + chunk - 1) / chunk) < (1ll << 31);
     int grid = h->B;
     if (queued) {

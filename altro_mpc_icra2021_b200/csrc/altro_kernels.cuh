@@ -87,8 +87,9 @@ __host__ __device__ constexpr Layout fixed_layout(int n, int m)
 // shared-memory row stride of a staged panel: rows whose length is a multiple of 8 doubles are padded by 4 so that the
 // four k-rows a DMMA fragment load touches fall into different banks (stride = 4 mod 8 doubles)
 __host__ __device__ constexpr int panel_ld(int ld) { return (ld % 8 == 0) ? ld + 4 : ld; }
-constexpr int PANEL_KC = 8;   // k-rows per staged operand panel
-constexpr int PANEL_NST = 3;  // stages in flight
+constexpr int PANEL_KC = 8;   // k-rows per staged operand panel (one bulk copy per row and operand, one lane each)
+constexpr int PANEL_NST = 5;  // stages in flight (measured: 8 x 5 beats 16 x 3 at the same bytes in flight)
+constexpr int PANEL_WT = 7;   // DMMA tile columns a consumer warp owns (32 x 56 accumulators = 112 registers; 200 = 4 x 7 x 8 - 24)
 
 __host__ __device__ inline Layout make_layout_big(int n, int m, int N, int P, int ncon, int EX, int tma = 1)
 {
@@ -106,10 +107,12 @@ __host__ __device__ inline Layout make_layout_big(int n, int m, int N, int P, in
     l.cand = q;
     q += q & 1;
     // TMA-staged panels: rows must be 16-byte multiples and K a multiple of 4 (n % 4 == 0); each stage holds
-    // PANEL_KC k-rows of both operands (+ 32 doubles of slack each: partial edge tiles read past the row end)
-    l.tma = (tma && n % 4 == 0 && n >= 32) ? 1 : 0;
+    // PANEL_KC k-rows of the left operand and of one column window (<= 8 PANEL_WT columns) of the right operand
+    // (+ 32 doubles of slack each: partial edge tiles read past the row end)
+    l.tma = (tma && n % 4 == 0 && n >= 32 && (m <= 8 * PANEL_WT || m % 2 == 0)) ? 1 : 0;
     if (l.tma) {
-        l.stage_doubles = PANEL_KC * (panel_ld(n) + panel_ld(n > m ? n : m)) + 64;
+        const int mx = n > m ? n : m, mx8 = (mx + 7) & ~7;
+        l.stage_doubles = PANEL_KC * ((mx + 4) + ((mx8 < 8 * PANEL_WT ? mx8 : 8 * PANEL_WT) + 4)) + 64;
         l.stage = take(PANEL_NST * l.stage_doubles);
         l.mbar = take(2 * PANEL_NST);
     }
@@ -188,6 +191,12 @@ struct Params {
     int *q_head, *q_done, *q_error;
     altro_opts_t o;
 };
+
+// fragment prefetch depth of Ctx::tile_gemm (k-steps of operands in flight per warp).  Measured at n = 200 (profiles/r2_large_n.md):
+// depth 1 (no explicit prefetch) 2076 solves/s, depth 2 / 3 / 4 1249 / 1329 / 1360 -- the extra live fragments spill.
+#ifndef ALTRO_GEMM_DEPTH
+#define ALTRO_GEMM_DEPTH 1
+#endif
 
 #ifdef __CUDACC__
 
@@ -337,10 +346,237 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the same on 32-bit shared-memory addresses (the panel loop keeps no generic pointers alive)
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t b, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 
 // Per-instance context: shared-memory pointers and problem view.
 // WIDE: the variant compiled into altro_solve_kernel_wide (whole register file, TMA-staged panels); the default kernels
 // do not carry that code.
+// ---- TMA-staged panel GEMM (large state dimension):
+//     C(i,j) = Ci(i,j) + sum_l PA[l][i] PB[l][j]  [+ sum_l PA2[l][i] PB2[l][j]],   every sum over ascending l.
+// The operands are "k-major" (row l of PA holds column l of the left factor; lda == M, ldb == Nc), so PANEL_KC
+// k-rows of an operand are one contiguous block of global memory.  The last warp of the CTA is the PRODUCER: it
+// streams the panels into a ring of PANEL_NST shared-memory stages with cp.async.bulk (one copy per k-row, issued
+// by one lane each, or one copy per panel when the rows need no padding); full[] barriers count the transaction
+// bytes, empty[] barriers one arrival per consumer warp.  The other NC = T/32 - 1 warps are CONSUMERS: C is cut
+// into column windows; inside a window a consumer owns 32 rows x up to PANEL_WT = 7 DMMA tiles = up to 28 independent
+// accumulator chains (4 A + 7 B fragment loads from shared memory feed 28 DMMAs per k-step).  With fewer than NC row
+// blocks the warps share a row block column-wise and the window widens accordingly (B'SA, 25 x 200, is one window).
+// A 200 x 200 x 200 product streams the left operand four times and the right operand once (1.6 MB from L2 instead
+// of 7 MB for the register-blocked tiles that read their operands where they are).  Each element's chain is the same
+// sequence of mma.sync.m8n8k4 steps over ascending l as in tile_gemm, so the bits do not change; K need not be a
+// multiple of 4: the fragments of the last, partial k-step are zero beyond K, exactly like tile_gemm's operand
+// functors.  S A uses PA = S: S is symmetric to the last bit (it is formed as (D + D')/2, commutative operations).
+// A free, non-inlined function: the product loop gets the whole register file (128 accumulator registers) and the
+// caller's live state is saved once per call instead of being spilled inside the loop.  Ci may be read transposed
+// (ci_t; square C only); the result goes to Co -- with Avg as (Avg + C)/2, the symmetrisation of the cost-to-go
+// Hessian fused into the last product -- and, if Co2 is given, Co2 = stored value + rho I (the regularised copy the
+// factorisation works on); all row-major with ld = Nc.  Returns the number of panels streamed.
+struct PanelArgs {
+    int M, Nc, K, K2, ci_t;
+    const double *PA, *PB, *PA2, *PB2, *Ci, *Avg;
+    double *Co, *Co2;
+    double rho;
+};
+template <int T>
+__device__ __noinline__ unsigned panel_gemm_fn(double *stage0, uint64_t *full, int sd, unsigned pg_count, const PanelArgs &ga)
+{
+    constexpr int NC = T / 32 - 1, WT = PANEL_WT;
+    const PanelArgs g = ga;  // a private copy: the stores below must not force the fields to be re-read
+    const double *__restrict__ const Ci = g.Ci, *__restrict__ const Avg = g.Avg;
+    double *__restrict__ const Co = g.Co, *__restrict__ const Co2 = g.Co2;
+    const int M = g.M, Nc = g.Nc, lda = M, ldb = Nc;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
+    uint64_t *empty = full + PANEL_NST;
+    const int lsa = panel_ld(lda), boff = PANEL_KC * lsa + 32;
+    const int ntc = (Nc + 7) >> 3, nrb = (M + 31) >> 5;
+    const int csplit = max(1, NC / nrb);                       // warps that share a row block
+    const int wcap = ((sd - 64) / PANEL_KC - lsa - 4) >> 3;     // tile columns of B a stage has room for
+    const int ns = (ntc + min(WT * csplit, wcap) - 1) / min(WT * csplit, wcap), nbw = (ntc + ns - 1) / ns;
+    const int nsub = min(csplit, nbw), tps = (nbw + nsub - 1) / nsub;
+    const int bpw = nrb * nsub, rpw = (bpw + NC - 1) / NC, rounds = ns * rpw;
+    const int lsb = ns == 1 ? panel_ld(ldb) : panel_ld(nbw * 8);  // row strides in shared memory
+    const int nch1 = (g.K + PANEL_KC - 1) / PANEL_KC, nchunk = nch1 + (g.K2 + PANEL_KC - 1) / PANEL_KC;
+    const int total = rounds * nchunk;
+    if (warp == NC) {
+        unsigned st = pg_count % PANEL_NST, use = pg_count / PANEL_NST;
+        int R = 0, cc = 0;
+#pragma unroll 1
+        for (int gi = 0; gi < total; ++gi) {
+            if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
+            const int second = cc >= nch1, c = second ? cc - nch1 : cc;
+            const int rows = min(PANEL_KC, (second ? g.K2 : g.K) - c * PANEL_KC);
+            const double *PA = second ? g.PA2 : g.PA, *PB = second ? g.PB2 : g.PB;
+            const int cb0 = (R / rpw) * nbw * 8, wc = ns == 1 ? ldb : min(nbw * 8, ldb - cb0);
+            double *As = stage0 + st * sd, *Bs = As + boff;
+            const uint32_t ba = (uint32_t)(rows * lda * sizeof(double)), bb = (uint32_t)(rows * wc * sizeof(double));
+            if (lane == 0) mbar_expect_tx(full + st, ba + bb);
+            __syncwarp();
+            if (lsa == lda) {
+                if (lane == 0) bulk_g2s(As, PA + (size_t)c * PANEL_KC * lda, ba, full + st);
+            } else if (lane < rows) {
+                bulk_g2s(As + lane * lsa, PA + ((size_t)c * PANEL_KC + lane) * lda, (uint32_t)(lda * sizeof(double)), full + st);
+            }
+            if (ns == 1 && lsb == ldb) {
+                if (lane == 16) bulk_g2s(Bs, PB + (size_t)c * PANEL_KC * ldb, bb, full + st);
+            } else if (lane >= 16 && lane - 16 < rows) {
+                bulk_g2s(Bs + (lane - 16) * lsb, PB + ((size_t)c * PANEL_KC + lane - 16) * ldb + cb0,
+                         (uint32_t)(wc * sizeof(double)), full + st);
+            }
+            if (++cc == nchunk) { cc = 0; ++R; }
+            if (++st == PANEL_NST) { st = 0; ++use; }
+        }
+    } else {
+        unsigned st = pg_count % PANEL_NST, par = (pg_count / PANEL_NST) & 1;
+        const uint32_t sbase = smem_u32(stage0), fbar = smem_u32(full), ebar = fbar + 8u * PANEL_NST;
+        const uint32_t sdb = (uint32_t)sd * 8u, sa4 = (uint32_t)lsa * 32u, sb4 = (uint32_t)lsb * 32u;  // bytes
+        const bool vec = (Nc & 1) == 0;  // rows start on 16-byte boundaries: two columns per load / store
+#pragma unroll 1
+        for (int R = 0; R < rounds; ++R) {
+            const int w = R / rpw, b = (R - w * rpw) * NC + warp;
+            const int rb = b / nsub, t0 = w * nbw + (b - rb * nsub) * tps;
+            const int ntile = b < bpw ? min(tps, min((w + 1) * nbw, ntc) - t0) : 0;  // <= 0: nothing to do this round
+            const int i0 = rb << 5, j0 = t0 << 3;
+            double acc[4][WT][2];
+            const bool civ = Ci && vec && !g.ci_t;
+#pragma unroll
+            for (int y = 0; y < WT; ++y)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = i0 + 8 * x + r, j = j0 + 8 * y + 2 * q;
+                    const bool in = y < ntile && i < M;
+                    if (civ) {  // two columns per load (j + 1 < Nc: Nc is even here)
+                        double2 v = make_double2(0.0, 0.0);
+                        if (in && j < Nc) v = *reinterpret_cast<const double2 *>(Ci + (size_t)i * Nc + j);
+                        acc[x][y][0] = v.x;
+                        acc[x][y][1] = v.y;
+                    } else {
+                        acc[x][y][0] = (Ci && in && j < Nc) ? Ci[g.ci_t ? (size_t)j * Nc + i : (size_t)i * Nc + j] : 0.0;
+                        acc[x][y][1] = (Ci && in && j + 1 < Nc) ? Ci[g.ci_t ? (size_t)(j + 1) * Nc + i : (size_t)i * Nc + j + 1] : 0.0;
+                    }
+                }
+            // the chunk loop keeps little state alive besides the accumulators: 32-bit shared-memory addresses, the ring
+            // position and a row countdown
+            const uint32_t a_off = (uint32_t)(q * lsa + i0 + r) * 8u, b_off = (uint32_t)(boff + q * lsb + (j0 - w * nbw * 8) + r) * 8u;
+            int krem = g.K, second = 0;
+#pragma unroll 1
+            for (int cc = 0; cc < nchunk; ++cc) {
+                mbar_wait_u32(fbar + 8u * st, par);
+                const int rows = min(PANEL_KC, krem);
+                if (ntile > 0) {
+                    uint32_t pa = sbase + st * sdb + a_off, pb = sbase + st * sdb + b_off;
+                    // every fragment load is unconditional (tile columns beyond ntile read stale shared memory that only
+                    // feeds skipped DMMAs): conditionally written fragment arrays would live in local memory
+                    auto kstep = [&](auto tail, bool live) {
+                        double a[4], bf[WT];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) a[x] = lds_f64(pa + 64u * x);
+#pragma unroll
+                        for (int y = 0; y < WT; ++y) bf[y] = lds_f64(pb + 64u * y);
+                        if constexpr (decltype(tail)::value) {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) a[x] = live ? a[x] : 0.0;
+#pragma unroll
+                            for (int y = 0; y < WT; ++y) bf[y] = live ? bf[y] : 0.0;
+                        }
+#pragma unroll
+                        for (int y = 0; y < WT; ++y)
+                            if (y < ntile) {
+#pragma unroll
+                                for (int x = 0; x < 4; ++x)
+                                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                                 : "+d"(acc[x][y][0]), "+d"(acc[x][y][1]) : "d"(a[x]), "d"(bf[y]));
+                            }
+                        pa += sa4;
+                        pb += sb4;
+                    };
+#pragma unroll 1
+                    for (int kk = 0; kk < (rows >> 2); ++kk) kstep(std::false_type{}, true);
+                    if (rows & 3) kstep(std::true_type{}, q < (rows & 3));  // k-rows beyond K contribute fma(0, 0, acc)
+                }
+                krem -= rows;
+                if (krem == 0 && !second) { krem = g.K2; second = 1; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_u32(ebar + 8u * st);
+                if (++st == PANEL_NST) { st = 0; par ^= 1; }
+            }
+            if (vec) {
+                // two tile columns at a time: all loads of the batch first (Avg), then the arithmetic and the stores
+#pragma unroll
+                for (int y0 = 0; y0 < WT; y0 += 2) {
+                    if (y0 >= ntile) break;
+                    double2 o[2][4];
+                    if (Avg) {
+#pragma unroll
+                        for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                const int i = i0 + 8 * x + r, j = j0 + 8 * (y0 + yy) + 2 * q;
+                                o[yy][x] = (y0 + yy < ntile && i < M && j < Nc)
+                                               ? *reinterpret_cast<const double2 *>(Avg + (size_t)i * Nc + j) : make_double2(0.0, 0.0);
+                            }
+                    }
+#pragma unroll
+                    for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const int i = i0 + 8 * x + r, j = j0 + 8 * (y0 + yy) + 2 * q;
+                            if (y0 + yy >= ntile || i >= M || j >= Nc) continue;
+                            double2 v = make_double2(acc[x][y0 + yy][0], acc[x][y0 + yy][1]);
+                            if (Avg) {
+                                v.x = 0.5 * (o[yy][x].x + v.x);
+                                v.y = 0.5 * (o[yy][x].y + v.y);
+                            }
+                            *reinterpret_cast<double2 *>(Co + (size_t)i * Nc + j) = v;
+                            if (Co2)
+                                *reinterpret_cast<double2 *>(Co2 + (size_t)i * Nc + j) =
+                                    make_double2(v.x + ((i == j) ? g.rho : 0.0), v.y + ((i == j + 1) ? g.rho : 0.0));
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int y = 0; y < WT; ++y)
+                    if (y < ntile) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const int i = i0 + 8 * x + r, j = j0 + 8 * y + 2 * q;
+                            if (i >= M) continue;
+                            const size_t e = (size_t)i * Nc + j;
+                            if (j < Nc) {
+                                const double v = Avg ? 0.5 * (Avg[e] + acc[x][y][0]) : acc[x][y][0];
+                                Co[e] = v;
+                                if (Co2) Co2[e] = v + ((i == j) ? g.rho : 0.0);
+                            }
+                            if (j + 1 < Nc) {
+                                const double v = Avg ? 0.5 * (Avg[e + 1] + acc[x][y][1]) : acc[x][y][1];
+                                Co[e + 1] = v;
+                                if (Co2) Co2[e + 1] = v + ((i == j + 1) ? g.rho : 0.0);
+                            }
+                        }
+                    }
+            }
+        }
+    }
+    // the results go to global memory through the generic proxy and are the next product's operands (async proxy)
+    fence_proxy_async();
+    __syncthreads();
+    return (unsigned)total;
+}
+
 template <int NX, int NU, int T, bool WIDE = false>
 struct Ctx {
     static constexpr bool ALL_SMEM = NX > 0 && NU > 0 && ALTRO_FIXED_ALL_SMEM;
@@ -382,14 +618,16 @@ struct Ctx {
             linv = sm + f.linv; mu = sm + f.mu; bc = sm + f.bc; red = sm + f.red; Qi = sm + f.Qi; X = sm + f.X;
         } else {
             // run-time sized kernel: large problems keep their n-sized matrices in a global workspace
-            double *big = l.big ? P.ws + (size_t)inst * l.ws_doubles : sm;
+            // (scratch of one solve, nothing in it survives a step: it belongs to the CTA, not to the instance, so that
+            // the persistent grid of a queued closed-loop run needs one workspace per resident CTA)
+            double *big = l.big ? P.ws + (size_t)blockIdx.x * l.ws_doubles : sm;
             Qd = sm + l.Qd; Qfd = sm + l.Qfd; Rd = sm + l.Rd; sA = big + l.sA; sB = big + l.sB; sd = sm + l.sd;
             S = big + l.S; SA = big + l.SA; Qxx = big + l.Qxx; SB = big + l.SB; Qux = big + l.Qux; T1 = big + l.T1;
             Quu = sm + l.Quu; L = sm + l.L; s = sm + l.s; Qx = sm + l.Qx; Qu = sm + l.Qu; t1 = sm + l.t1;
             linv = sm + l.linv; mu = sm + l.mu; bc = sm + l.bc; red = sm + l.red; Qi = big + l.Qi; X = sm + l.X;
         }
         U = sm + l.U; Xb = sm + l.Xb; Ub = sm + l.Ub;
-        K = ((NX == 0 && l.big) ? P.ws + (size_t)inst * l.ws_doubles : sm) + l.K; dv = sm + l.dv; lam = sm + l.lam;
+        K = ((NX == 0 && l.big) ? P.ws + (size_t)blockIdx.x * l.ws_doubles : sm) + l.K; dv = sm + l.dv; lam = sm + l.lam;
         if constexpr (ALL_SMEM) {
             // fixed-dimension kernels keep the reference window and the expansion blocks in shared memory, always
             // (the host routes problems that do not fit to the run-time sized kernel): every access is an LDS/STS
@@ -467,7 +705,7 @@ struct Ctx {
         if constexpr (WIDE) {
             if (P.lay.big && P.lay.tma && tid == 0) {  // panel pipeline barriers (panel_gemm)
                 uint64_t *mb = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_base) + P.lay.mbar);
-                for (int i = 0; i < PANEL_NST; ++i) { mbar_init(mb + i, 1); mbar_init(mb + PANEL_NST + i, T / 32); }
+                for (int i = 0; i < PANEL_NST; ++i) { mbar_init(mb + i, 1); mbar_init(mb + PANEL_NST + i, T / 32 - 1); }
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
         }
@@ -994,20 +1232,35 @@ struct Ctx {
                                  : "+d"(c[1][b][0]), "+d"(c[1][b][1]) : "d"(x1), "d"(y[b]));
                 }
             };
-#pragma unroll 2
-            for (int k0 = 0; k0 < K1; k0 += 4) {
-                double y[NB];
+            // Software pipeline: the fragments of k-step s + D - 1 are requested before the DMMAs of k-step s are issued,
+            // so D - 1 k-steps of tensor work cover the L2 latency of the operand loads (the operands of this path live in
+            // the per-instance global workspace).  The chain order of every element is unchanged.
+            auto chain = [&](int K, auto &&fa, auto &&fb) {
+                constexpr int D = ALTRO_GEMM_DEPTH;
+                double xa[D][2], ya[D][NB];
+                auto fetch = [&](int k, double (&x)[2], double (&y)[NB]) {
+                    x[0] = fa(i0 + r, k + q);
+                    x[1] = fa(i0 + 8 + r, k + q);
 #pragma unroll
-                for (int b = 0; b < NB; ++b) y[b] = b1(k0 + q, j0 + 8 * b + r);
-                step(a1(i0 + r, k0 + q), a1(i0 + 8 + r, k0 + q), y);
-            }
-#pragma unroll 2
-            for (int k0 = 0; k0 < K2; k0 += 4) {
-                double y[NB];
+                    for (int b = 0; b < NB; ++b) y[b] = fb(k + q, j0 + 8 * b + r);
+                };
 #pragma unroll
-                for (int b = 0; b < NB; ++b) y[b] = b2(k0 + q, j0 + 8 * b + r);
-                step(a2(i0 + r, k0 + q), a2(i0 + 8 + r, k0 + q), y);
-            }
+                for (int s = 0; s < D - 1; ++s)
+                    if (4 * s < K) fetch(4 * s, xa[s], ya[s]);
+#pragma unroll 1
+                for (int k0 = 0; k0 < K; k0 += 4 * D) {
+#pragma unroll
+                    for (int s = 0; s < D; ++s) {
+                        const int k = k0 + 4 * s;
+                        if (k < K) {
+                            if (k + 4 * (D - 1) < K) fetch(k + 4 * (D - 1), xa[(s + D - 1) % D], ya[(s + D - 1) % D]);
+                            step(xa[s][0], xa[s][1], ya[s]);
+                        }
+                    }
+                }
+            };
+            chain(K1, a1, b1);
+            chain(K2, a2, b2);
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -1018,100 +1271,18 @@ struct Ctx {
         }
     }
 
-    // ---- TMA-staged panel GEMM (large state dimension):  C(i,j) = init(i,j) + sum_l PA[l][i] PB[l][j],  l ascending.
-    // Both operands are "k-major" (row l of PA holds column l of the left factor), so a panel of PANEL_KC k-rows of
-    // each is ONE contiguous block in global memory and goes to shared memory with one cp.async.bulk per operand,
-    // PANEL_NST panels in flight behind mbarriers (full: transaction bytes; empty: one arrival per warp).  A warp owns a
-    // 32 x 32 block of C (4 x 4 DMMA tiles, 16 independent accumulator chains per k-step fed by 8 shared-memory
-    // fragment loads); the blocks of a round (one per warp) share every panel.  Each element's chain is the same
-    // sequence of mma.sync.m8n8k4 steps over ascending l as in tile_gemm, so the bits do not change.
-    // S A uses PA = S: S is symmetric to the last bit (it is formed as (D + D')/2 with commutative operations).
-    template <class FI, class FS>
-    __device__ __forceinline__ void panel_gemm(int M, int Nc, int K, const double *PA, int lda, const double *PB, int ldb,
-                                               FI init, FS store)
+    // see panel_gemm_fn
+    __device__ __forceinline__ void panel_gemm(const PanelArgs &g)
     {
-        constexpr int NW = T / 32;
-        const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
         double *stage0 = reinterpret_cast<double *>(smem_base) + P.lay.stage;
-        uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_base) + P.lay.mbar), *empty = full + PANEL_NST;
-        const int lsa = panel_ld(lda), lsb = panel_ld(ldb);  // row strides in shared memory
-        const int sd = P.lay.stage_doubles, boff = PANEL_KC * lsa + 32;
-        const int nbc = (Nc + 31) >> 5, nblk = ((M + 31) >> 5) * nbc, rounds = (nblk + NW - 1) / NW;
-        const int nchunk = (K + PANEL_KC - 1) / PANEL_KC, total = rounds * nchunk;
-        auto issue = [&](int g) {  // thread 0: panel g of this call into its stage
-            const unsigned G = pg_count + g, st = G % PANEL_NST, use = G / PANEL_NST;
-            if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
-            const int c = g % nchunk, rows = min(PANEL_KC, K - c * PANEL_KC);
-            double *As = stage0 + st * sd, *Bs = As + boff;
-            const uint32_t ba = (uint32_t)(rows * lda * sizeof(double)), bb = (uint32_t)(rows * ldb * sizeof(double));
-            mbar_expect_tx(full + st, ba + bb);
-            if (lsa == lda) bulk_g2s(As, PA + (size_t)c * PANEL_KC * lda, ba, full + st);
-            else
-                for (int rr = 0; rr < rows; ++rr)
-                    bulk_g2s(As + rr * lsa, PA + ((size_t)c * PANEL_KC + rr) * lda, (uint32_t)(lda * sizeof(double)), full + st);
-            if (lsb == ldb) bulk_g2s(Bs, PB + (size_t)c * PANEL_KC * ldb, bb, full + st);
-            else
-                for (int rr = 0; rr < rows; ++rr)
-                    bulk_g2s(Bs + rr * lsb, PB + ((size_t)c * PANEL_KC + rr) * ldb, (uint32_t)(ldb * sizeof(double)), full + st);
-        };
-        if (tid == 0)
-            for (int g = 0; g < PANEL_NST - 1 && g < total; ++g) issue(g);
-        double acc[4][4][2];
-        int i0 = 0, j0 = 0;
-        bool active = false;
-#pragma unroll 1
-        for (int g = 0; g < total; ++g) {
-            if (tid == 0 && g + PANEL_NST - 1 < total) issue(g + PANEL_NST - 1);
-            const int c = g % nchunk;
-            if (c == 0) {
-                const int b = (g / nchunk) * NW + warp;
-                active = b < nblk;
-                i0 = (b / nbc) << 5;
-                j0 = (b - (b / nbc) * nbc) << 5;
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        acc[x][y][0] = active ? init(i0 + 8 * x + r, j0 + 8 * y + 2 * q) : 0.0;
-                        acc[x][y][1] = active ? init(i0 + 8 * x + r, j0 + 8 * y + 2 * q + 1) : 0.0;
-                    }
-            }
-            const unsigned G = pg_count + g, st = G % PANEL_NST, use = G / PANEL_NST;
-            mbar_wait(full + st, use & 1);
-            if (active) {
-                const double *As = stage0 + st * sd, *Bs = As + boff;
-                const int steps = min(PANEL_KC, K - c * PANEL_KC) >> 2;
-#pragma unroll 2
-                for (int kk = 0; kk < steps; ++kk) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) a[x] = As[(kk * 4 + q) * lsa + i0 + 8 * x + r];
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) b[y] = Bs[(kk * 4 + q) * lsb + j0 + 8 * y + r];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y)
-                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                         : "+d"(acc[x][y][0]), "+d"(acc[x][y][1]) : "d"(a[x]), "d"(b[y]));
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + st);
-            if (c == nchunk - 1 && active) {
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        store(i0 + 8 * x + r, j0 + 8 * y + 2 * q, acc[x][y][0]);
-                        store(i0 + 8 * x + r, j0 + 8 * y + 2 * q + 1, acc[x][y][1]);
-                    }
-            }
-        }
-        pg_count += total;
-        // the results go to global memory through the generic proxy and are the next product's operands (async proxy)
-        fence_proxy_async();
-        __syncthreads();
+        uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smem_base) + P.lay.mbar);
+        pg_count += panel_gemm_fn<T>(stage0, full, P.lay.stage_doubles, pg_count, g);
+    }
+    __device__ __forceinline__ void panel_gemm(int M, int Nc, int K, const double *PA, const double *PB, const double *Ci,
+                                               double *Co, double *Co2 = nullptr, double rho2 = 0.0)
+    {
+        PanelArgs g{M, Nc, K, 0, 0, PA, PB, nullptr, nullptr, Ci, nullptr, Co, Co2, rho2};
+        panel_gemm(g);
     }
 
     // Returns false if Quu could not be made positive definite.
@@ -1165,10 +1336,8 @@ struct Ctx {
                     if constexpr (WIDE) {
                         fence_proxy_async();  // S (and the first knot's terminal S) was written with ordinary stores
                         __syncthreads();
-                        panel_gemm(n, n, n, S, n, A, n, [](int, int) { return 0.0; },
-                                   [&](int i, int j, double v) { if (i < n && j < n) SA[i * n + j] = v; });
-                        panel_gemm(n, m, n, S, n, Bm, m, [](int, int) { return 0.0; },
-                                   [&](int i, int j, double v) { if (i < n && j < m) SB[i * m + j] = v; });
+                        panel_gemm(n, n, n, S, A, nullptr, SA);
+                        panel_gemm(n, m, n, S, Bm, nullptr, SB);
                     }
                 } else if (big) {
                     tile_gemm(n, n, [](int, int) { return 0.0; }, n,
@@ -1211,25 +1380,20 @@ struct Ctx {
                 const int nt_xx = tn * tn1, nt_ux = tm * tn, nt_uu = tm * tm1;
                 if (tma) {
                     if constexpr (WIDE) {
-                        panel_gemm(n, n, n, A, n, SA, n,
-                                   [&](int i, int j) { return (i < n && j < n) ? Qi[oQxx + i * n + j] : 0.0; },
-                                   [&](int i, int j, double v) { if (i < n && j < n) Qxx[i * n + j] = v; });
-                        panel_gemm(m, n, n, Bm, m, SA, n, [](int, int) { return 0.0; },
-                                   [&](int i, int j, double v) { if (i < m && j < n) Qux[i * n + j] = v; });
-                        panel_gemm(m, m, n, Bm, m, SB, m,
-                                   [&](int i, int j) { return (i < m && j < m) ? Qi[oQuu + i * m + j] : 0.0; },
-                                   [&](int i, int j, double v) {
-                                       if (i < m && j < m) { Quu[i * m + j] = v; L[i * m + j] = v + ((i == j) ? rho : 0.0); }
-                                   });
+                        panel_gemm(n, n, n, A, SA, Qi + oQxx, Qxx);
+                        panel_gemm(m, n, n, Bm, SA, nullptr, Qux);
+                        panel_gemm(m, m, n, Bm, SB, Qi + oQuu, Quu, L, rho);
                         // the vector columns of the two tiles: Qx = Qi + A's, Qu = Qi + B's (same chains, one thread each)
                         for (int i = tid; i < n + m; i += T) {
                             if (i < n) {
                                 double acc = Qi[i];
+#pragma unroll 8
                                 for (int l = 0; l < n; ++l) acc = fma(A[l * n + i], s[l], acc);
                                 Qx[i] = acc;
                             } else {
                                 const int iu = i - n;
                                 double acc = Qi[oQu + iu];
+#pragma unroll 8
                                 for (int l = 0; l < n; ++l) acc = fma(Bm[l * m + iu], s[l], acc);
                                 Qu[iu] = acc;
                             }
@@ -1464,7 +1628,25 @@ struct Ctx {
                 ALTRO_TICK(5);
                 // P6: [S' | s] = [Qxx | Qx] + K'[T1 | t1] + Qux'[K | d]; the transposed tile is chained in the same
                 //     lanes so that S = (S' + S'^T)/2 needs no second pass.  dV += [d'Qu, 1/2 d'Quu d].
-                if (big) {
+                if (tma) {
+                    // the same chains through the staged panels: D = Qxx + K'T1 + Qux'K into SA, E = Qxx' + T1'K + K'Qux
+                    // with the symmetrisation S = (D + E)/2 fused into the last store; the vector column by plain chains
+                    if constexpr (WIDE) {
+                        fence_proxy_async();  // K, T1 were written with ordinary stores
+                        __syncthreads();
+                        panel_gemm(PanelArgs{n, n, m, m, 0, Kk, T1, Qux, Kk, Qxx, nullptr, SA, nullptr, 0.0});
+                        panel_gemm(PanelArgs{n, n, m, m, 1, T1, Kk, Kk, Qux, Qxx, SA, S, nullptr, 0.0});
+#pragma unroll 1
+                        for (int i = tid; i < n; i += T) {
+                            double acc = Qx[i];
+#pragma unroll 8
+                            for (int l = 0; l < m; ++l) acc = fma(Kk[l * n + i], t1[l], acc);
+#pragma unroll 8
+                            for (int l = 0; l < m; ++l) acc = fma(Qux[l * n + i], dk_[l], acc);
+                            s[i] = acc;
+                        }
+                    }
+                } else if (big) {
                     // D = [Qxx | Qx] + K'[T1 | t1] + Qux'[K | d] into SA (free since P2) and s; E = Qxx' + T1'K + K'Qux
                     // into S (not read since P1); then S = (D + E)/2 element by element.
                     tile_gemm(n, n + 1,
