@@ -447,9 +447,11 @@ int finalize(altro_handle_t h)
     if ((size_t)h->lay.bytes > limit || (big_env ? atoi(big_env) != 0 : lonely)) {
         // Large state dimension: n-sized matrices and gains in a per-instance global workspace (make_layout_big).
         if (h->ex_glob == nullptr && EX > 0) CK(h, dalloc(&h->ex_glob, (size_t)B * EX));
-        // TMA-staged operand panels (Ctx::panel_gemm): bit-identical, but measured SLOWER than the register-blocked tiles
-        // fed from L2 (profiles/r2_large_n.md: 877-992 vs 1383 solves/s at n = 200), so opt-in: ALTRO_B200_TMA=1
-        int want_tma = 0;
+        // TMA-staged operand panels (panel_gemm_fn, one CTA per SM with the whole register file): bit-identical to the
+        // register-blocked tiles fed from L2 (two CTAs per SM); measured (profiles/r2_large_n.md, 296 instances):
+        // n = 200 2915 vs 2126 solves/s, n = 128 5535 vs 5643, n = 100 8015 vs 8184, n = 64 15.2k vs 23.6k -- so the
+        // staged path takes over from n = 160.  ALTRO_B200_TMA=0/1 forces either.
+        int want_tma = (T == 256 && n >= 160) ? 1 : 0;
         if (const char *e = getenv("ALTRO_B200_TMA")) want_tma = (T == 256 && atoi(e)) ? 1 : 0;
         Layout lb = make_layout_big(n, m, N, P, ncons, 0, want_tma);
         if ((size_t)lb.bytes > limit && lb.tma) lb = make_layout_big(n, m, N, P, ncons, 0, 0);  // no room for the panel stages

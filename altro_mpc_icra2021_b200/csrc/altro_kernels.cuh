@@ -88,7 +88,10 @@ __host__ __device__ constexpr Layout fixed_layout(int n, int m)
 // four k-rows a DMMA fragment load touches fall into different banks (stride = 4 mod 8 doubles)
 __host__ __device__ constexpr int panel_ld(int ld) { return (ld % 8 == 0) ? ld + 4 : ld; }
 constexpr int PANEL_KC = 8;   // k-rows per staged operand panel (one bulk copy per row and operand, one lane each)
-constexpr int PANEL_NST = 5;  // stages in flight (measured: 8 x 5 beats 16 x 3 at the same bytes in flight)
+#ifndef ALTRO_PANEL_NST
+#define ALTRO_PANEL_NST 5
+#endif
+constexpr int PANEL_NST = ALTRO_PANEL_NST;  // stages in flight (measured: 8 x 5 beats 16 x 3 at the same bytes in flight)
 constexpr int PANEL_WT = 7;   // DMMA tile columns a consumer warp owns (32 x 56 accumulators = 112 registers; 200 = 4 x 7 x 8 - 24)
 
 __host__ __device__ inline Layout make_layout_big(int n, int m, int N, int P, int ncon, int EX, int tma = 1)
