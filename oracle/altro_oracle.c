@@ -1,7 +1,9 @@
 /*
  * altro_oracle.c -- CPU restatement of the ALTRO AL-iLQR solve path.  See altro_oracle.h:
- * TEST INFRASTRUCTURE ONLY, PARITY UNPINNED (un-vendored Altro.jl 0.2.0@socp /
- * TrajectoryOptimization.jl 0.3.2@socp; algorithm per SURVEY.md Appendix A).
+ * TEST INFRASTRUCTURE ONLY, PARITY UNPINNED bit for bit (un-vendored Altro.jl 0.2.0@socp /
+ * TrajectoryOptimization.jl 0.3.2@socp; algorithm per SURVEY.md Appendix A).  What is pinned: the iteration
+ * statistics of the reference's own saved benchmark runs (tests/golden/reference_stats.json, extracted from
+ * benchmarks/**.jld2 by tests/golden/extract_reference_stats.py; tests/test_oracle_solutions.py).
  *
  * One instance is solved at a time by plain scalar loops; orc_solve_batch distributes
  * instances over pthreads pulling from a shared counter (the analogue of Threads.@threads over the batch).
