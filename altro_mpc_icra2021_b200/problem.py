@@ -463,7 +463,8 @@ class SolverOptions:
     # the initial rollout's cost is not a line-search reference: the first forward pass of every iLQR solve takes
     # its full step (J_prev = +inf).  Matches the saved grasp statistics of the reference
     first_step_unconditional: bool = True
-    # accepted for API compatibility; this path has no projected-Newton polish / static variant / logging
+    # accepted for API compatibility (static variant, logging); projected_newton = True is refused at upload:
+    # the polish step is not built and every benchmark of the reference switches it off
     projected_newton: bool = False
     static_bp: bool = True
     verbose: int = 0

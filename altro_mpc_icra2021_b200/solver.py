@@ -180,6 +180,10 @@ class ALTROSolver:
         self._opts_dirty = True
 
     def _push_options(self) -> None:
+        if self.opts.projected_newton:
+            # every benchmark of the reference sets projected_newton = false; the polish step is not built and is not
+            # silently skipped either
+            raise AltroError("projected_newton = true is not supported by this solve path (DESIGN.md section 7)")
         o = AltroOpts()
         for name, _ in AltroOpts._fields_:
             setattr(o, name, getattr(self.opts, name))

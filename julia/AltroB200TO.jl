@@ -22,8 +22,24 @@ const TO = TrajectoryOptimization
 const RD = RobotDynamics
 
 include("AltroB200.jl")
-import .AltroB200: SolverOptions, EQUALITY, INEQUALITY, SECOND_ORDER_CONE, STATE, CONTROL
+import .AltroB200: EQUALITY, INEQUALITY, SECOND_ORDER_CONE, STATE, CONTROL
 const LL = AltroB200
+
+# Altro.SolverOptions as the scripts construct it (run_random_linear.jl:41-49, run_simple_rocket.jl:121-129,
+# ALTROParams.jl:86-95): every field of the C struct (LL.SolverOptions, same names, types and defaults) plus the
+# keywords the scripts pass that have no counterpart on this path.  projected_newton = true is refused at upload (the
+# polish step is not built; every benchmark sets it false); static_bp, verbose and show_summary are accepted and ignored.
+@eval Base.@kwdef mutable struct SolverOptions
+    $([:($f::$(fieldtype(LL.SolverOptions, f)) = $(getfield(LL.SolverOptions(), f))) for f in fieldnames(LL.SolverOptions)]...)
+    projected_newton::Bool = false
+    static_bp::Bool = true
+    verbose::Int = 0
+    show_summary::Bool = false
+end
+function ll_options(o::SolverOptions)
+    o.projected_newton && error("AltroB200: projected_newton = true is not supported by this solve path")
+    return LL.SolverOptions(; (f => getfield(o, f) for f in fieldnames(LL.SolverOptions))...)
+end
 
 export ALTROSolver, SolverOptions, solve!, set_options!, iterations, status, states, controls, cost, max_violation,
        benchmark_solve!, get_constraints, get_trajectory, shift_fill!
@@ -196,7 +212,7 @@ function ALTROSolver(probs::Vector{<:TO.Problem}, opts::SolverOptions=SolverOpti
         x0[:, b] = p.x0
         for k in 1:N-1; U0[:, k, b] = RD.control(p.Z[k]); end
     end
-    ll = LL.ALTROSolver(n, m, N, B, dt; A=A, Bm=Bm, d=d, Q=Q, R=R, Qf=Qf, Xref=Xref, Uref=Uref, x0=x0, U0=U0, opts=opts, device=device)
+    ll = LL.ALTROSolver(n, m, N, B, dt; A=A, Bm=Bm, d=d, Q=Q, R=R, Qf=Qf, Xref=Xref, Uref=Uref, x0=x0, U0=U0, opts=ll_options(opts), device=device)
     blocks = Tuple{Any,UnitRange{Int},Block,Int}[]
     for (inds, con) in zip(p1.constraints)
         for (blk, kn) in lower(con, inds, n, m, N)
@@ -284,7 +300,7 @@ end
 
 "solve!(solver): re-read the shared Problems, batched AL-iLQR solve on the GPU, write the solution back into prob.Z."
 function solve!(s::ALTROSolver)
-    s.ll.opts = s.opts
+    s.ll.opts = ll_options(s.opts)
     refresh!(s)
     LL.solve!(s.ll)
     n, m, N = size(s.probs[1])

@@ -75,6 +75,18 @@ def test_options_copy_is_independent():
     assert a.cost_tolerance == 1e-3 and a.penalty_scaling == 10.0 and a.iterations_outer == 30
 
 
+def test_projected_newton_is_refused_not_ignored():
+    """The polish step is not built (every benchmark of the reference sets projected_newton = false): asking for it is
+    an error at option upload, before any device call."""
+    from altro_mpc_icra2021_b200.solver import ALTROSolver, AltroError
+
+    sv = ALTROSolver.__new__(ALTROSolver)  # no library, no device: _push_options must fail before touching either
+    sv.opts = SolverOptions(projected_newton=True)
+    with pytest.raises(AltroError, match="projected_newton"):
+        sv._push_options()
+    sv.h = None
+
+
 @pytest.mark.parametrize("total,world", [(4096, 8), (10, 3), (5, 8), (1, 1)])
 def test_shard_ranges_partition_the_batch(total, world):
     edges = [sharding.shard_range(total, r, world) for r in range(world)]
