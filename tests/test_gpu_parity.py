@@ -199,6 +199,48 @@ def test_large_state_dimensions_use_the_global_workspace(n, m, N):
     assert g.launch_info()["smem_bytes"] < 227 * 1024
 
 
+@pytest.mark.parametrize("n,m,N", [(64, 16, 7), (96, 7, 6), (100, 25, 5), (160, 20, 5), (200, 25, 4)])
+def test_staged_panel_gemm_and_direct_tiles_give_the_same_bits(n, m, N, monkeypatch):
+    """The large-dimension Riccati products through TMA-staged operand panels (panel_gemm_fn: cp.async.bulk + mbarrier
+    ring, producer warp, chained products, fused symmetrisation) and through the direct L2-operand tiles: both equal the
+    oracle bit for bit.  Covers m not a multiple of 4 (partial last k-step of the K = m products), odd m (scalar
+    prologue / epilogue of the m-wide outputs) and even m (16-byte path), one and several column windows."""
+    info = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("ALTRO_B200_TMA", tma)
+        prob = lqr_problem(n=n, m=m, N=N, batch=3, seed=n + m, u_bnd=0.4)
+        _, g, _ = solve_both(prob, SolverOptions(constraint_tolerance=1e-6))
+        info[tma] = g.launch_info()
+        g.close()
+    assert info["1"]["smem_bytes"] > info["0"]["smem_bytes"]  # the panel stages are part of the staged layout only
+    assert info["1"]["ctas_per_sm"] == 1
+
+
+def test_staged_panel_path_in_a_queued_closed_loop_run(monkeypatch):
+    """Closed-loop run of a large-dimension batch through the work queue (workspace bound to the CTA slot, state
+    carried through global memory between the items of an instance) against the oracle's run."""
+    from oracle.oracle import OracleProblem
+
+    monkeypatch.setenv("ALTRO_B200_TMA", "1")
+    n, m, K, B = 96, 12, 3, 5
+    prob, Xt, Ut, ks = random_linear.mpc_problem(n, m, 9, batch=B, seed=31)
+    opts = random_linear.mpc_options()
+    pg = copy.deepcopy(prob)
+    sv = gpu_solver(pg, opts)
+    sv.set_track(Xt, Ut, ks)
+    noise = mpc.rng_for(n, m).standard_normal((K, B, n))
+    sv.set_noise_model(1, 0.01, 0.0)
+    sv.set_noise_bank(noise)
+    sv.solve()
+    rg = sv.mpc_run(K)
+    op = OracleProblem(prob)
+    op.solve(opts, 4)
+    ro = op.mpc_run(opts, K, noise, (1, 0.01, 0.0), (Xt, Ut), ks, True, 4)
+    for k in ro:
+        assert np.array_equal(rg[k], ro[k]), k
+    assert np.array_equal(pg.X, prob.X) and np.array_equal(pg.U, prob.U)
+
+
 # ------------------------------------------------------------------ edge cases
 
 def test_single_instance_and_unconstrained():
