@@ -255,69 +255,113 @@ __device__ __forceinline__ double gmax(double v, double *red)
     return s;
 }
 
-// LDL' of the m x m matrix in L (un-normalised lower factor X, reciprocal pivots r) and
-// [K | d] = -(L D L')^-1 [Qux | Qu] for a medium control dimension (quadruped m = 12, random linear m = 6), kept
-// out of line so that its register arrays get a register allocation of their own.  Lane i of warp 0 keeps row i
-// of the factor in registers and fetches the pivot row with shuffles (no shared-memory round trip per column);
-// the factor then goes to shared memory once and every right-hand side is substituted in registers by one thread.
-// Same fma / multiply sequence as the oracle's scalar loops.  Called by warp 0 only (the other warps prepare the
-// next knot meanwhile); returns true if a pivot is not positive.
+// LDL' of the m x m block L (4 < m <= 16) and [K | d] = -L^-1 [Qux | Qu], warp 0, kept out of line so that its
+// register arrays get a register allocation of their own.  Element (i, j) of the un-normalised factor accumulates
+// L_ij - sum_l X_il (X_jl r_l) over ascending l with reciprocal pivots r_l = 1/X_ll (the oracle's chains), in a
+// right-looking order: once pivot l is known, all remaining entries take one independent fma each, so only
+// pivot -> reciprocal -> product -> one fma is on the dependent path.
+//  * m > 8 (quadruped, m = 12): EVERY lane factorises the whole block in its own registers -- no shuffle, no
+//    shared-memory round trip (the row-per-lane version with shuffled pivot rows was half of a quadruped knot);
+//  * m <= 8 (grasp, random linear, m = 6): lane i keeps row i and the pivot-row products travel by shuffle (measured:
+//    the register-resident form costs the m = 6 kernels 20-30 % through the caller's spills around the call).
+// Then lane c substitutes right-hand side c: forward y = L^-1 b, z = y r, backward (q descending).
 template <int MM>
-__device__ __noinline__ bool ldl_solve_medium(double *L, double *linv, const double *Qux, const double *Qu, double *Kk,
-                                              double *dk_, int n)
+__device__ __noinline__ bool ldl_solve_medium(double *L, const double *Qux, const double *Qu, double *Kk, double *dk_, int n)
 {
     const int lane = threadIdx.x & 31;
-    bool bad = false;
-    double row[MM], rr[MM];
-    const int li = lane < MM ? lane : MM - 1;
+    if constexpr (MM > 8) {
+        double X[MM * (MM + 1) / 2], rr[MM];
+#define ALTRO_TRI(i, j) X[(i) * ((i) + 1) / 2 + (j)]
 #pragma unroll
-    for (int j = 0; j < MM; ++j) row[j] = L[li * MM + j];
+        for (int i = 0; i < MM; ++i)
 #pragma unroll
-    for (int j = 0; j < MM; ++j) {
-        double acc = row[j];
+            for (int j = 0; j <= i; ++j) ALTRO_TRI(i, j) = L[i * MM + j];
 #pragma unroll
-        for (int l = 0; l < j; ++l) acc = fma(-row[l], __shfl_sync(0xffffffffu, row[l], j) * rr[l], acc);
-        row[j] = acc;
-        const double piv = __shfl_sync(0xffffffffu, acc, j);
-        if (!(piv > 0.0)) { bad = true; break; }
-        rr[j] = __drcp_rn(piv);
-    }
-    if (bad) return true;
-    if (lane < MM) {
+        for (int l = 0; l < MM; ++l) {
+            if (!(ALTRO_TRI(l, l) > 0.0)) return true;  // the same value in every lane
+            rr[l] = __drcp_rn(ALTRO_TRI(l, l));
 #pragma unroll
-        for (int j = 0; j < MM; ++j) L[lane * MM + j] = row[j];
-    }
-    if (lane == 0) {
+            for (int j = l + 1; j < MM; ++j) {
+                const double t = ALTRO_TRI(j, l) * rr[l];
 #pragma unroll
-        for (int j = 0; j < MM; ++j) linv[j] = rr[j];
-    }
-    __syncwarp();
+                for (int i = j; i < MM; ++i) ALTRO_TRI(i, j) = fma(-ALTRO_TRI(i, l), t, ALTRO_TRI(i, j));
+            }
+        }
 #pragma unroll 1
-    for (int c = lane; c <= n; c += 32) {
-        double *bp = (c < n) ? Kk + c : dk_;
-        const double *src = (c < n) ? Qux + c : Qu;
-        const int st = (c < n) ? n : 1;
-        double bb[MM];
+        for (int c = lane; c <= n; c += 32) {
+            double *bp = (c < n) ? Kk + c : dk_;
+            const double *src = (c < n) ? Qux + c : Qu;
+            const int st = (c < n) ? n : 1;
+            double bb[MM];
 #pragma unroll
-        for (int i = 0; i < MM; ++i) {
-            double acc = -src[i * st];
+            for (int i = 0; i < MM; ++i) {
+                double acc = -src[i * st];
 #pragma unroll
-            for (int l = 0; l < i; ++l) acc = fma(-L[i * MM + l], bb[l] * rr[l], acc);
-            bb[i] = acc;
+                for (int l = 0; l < i; ++l) acc = fma(-ALTRO_TRI(i, l), bb[l] * rr[l], acc);
+                bb[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
+#pragma unroll
+            for (int i = MM - 1; i >= 0; --i) {
+                double acc2 = 0.0;
+#pragma unroll
+                for (int l = MM - 1; l > i; --l) acc2 = fma(ALTRO_TRI(l, i), bb[l], acc2);
+                bb[i] = fma(-rr[i], acc2, bb[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
         }
+#undef ALTRO_TRI
+        return false;
+    } else {
+        bool bad = false;
+        double row[MM], rr[MM];
+        const int li = lane < MM ? lane : MM - 1;
 #pragma unroll
-        for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
+        for (int j = 0; j < MM; ++j) row[j] = L[li * MM + j];
 #pragma unroll
-        for (int i = MM - 1; i >= 0; --i) {
-            double acc2 = 0.0;
+        for (int l = 0; l < MM; ++l) {
+            const double piv = __shfl_sync(0xffffffffu, row[l], l);
+            if (!(piv > 0.0)) { bad = true; break; }
+            rr[l] = __drcp_rn(piv);
+            const double t = row[l] * rr[l];
 #pragma unroll
-            for (int l = MM - 1; l > i; --l) acc2 = fma(L[l * MM + i], bb[l], acc2);
-            bb[i] = fma(-rr[i], acc2, bb[i]);
+            for (int j = l + 1; j < MM; ++j) row[j] = fma(-row[l], __shfl_sync(0xffffffffu, t, j), row[j]);
         }
+        if (bad) return true;
+        if (lane < MM) {
 #pragma unroll
-        for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
+            for (int j = 0; j < MM; ++j) L[lane * MM + j] = row[j];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int c = lane; c <= n; c += 32) {
+            double *bp = (c < n) ? Kk + c : dk_;
+            const double *src = (c < n) ? Qux + c : Qu;
+            const int st = (c < n) ? n : 1;
+            double bb[MM];
+#pragma unroll
+            for (int i = 0; i < MM; ++i) {
+                double acc = -src[i * st];
+#pragma unroll
+                for (int l = 0; l < i; ++l) acc = fma(-L[i * MM + l], bb[l] * rr[l], acc);
+                bb[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
+#pragma unroll
+            for (int i = MM - 1; i >= 0; --i) {
+                double acc2 = 0.0;
+#pragma unroll
+                for (int l = MM - 1; l > i; --l) acc2 = fma(L[l * MM + i], bb[l], acc2);
+                bb[i] = fma(-rr[i], acc2, bb[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
+        }
+        return false;
     }
-    return false;
 }
 
 // ---- TMA bulk copies and mbarriers (sm_90+ PTX): operand panels of the large-dimension GEMMs are fetched by the copy
@@ -1529,7 +1573,7 @@ struct Ctx {
                                 }
                             }
                         } else {
-                            bad = ldl_solve_medium<(NU > 4 && NU <= 16) ? NU : 5>(L, linv, Qux, Qu, Kk, dk_, n);
+                            bad = ldl_solve_medium<(NU > 4 && NU <= 16) ? NU : 5>(L, Qux, Qu, Kk, dk_, n);
                         }
                         if (T > 32 && lane == 0) bc[5] = bad ? 1.0 : 0.0;
                         if (T == 32 && !bad && k > 0) prep_knot(k - 1, tid, T);
