@@ -276,12 +276,22 @@ __device__ __noinline__ bool ldl_solve_medium(double *L, const double *Qux, cons
         for (int i = 0; i < MM; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) ALTRO_TRI(i, j) = L[i * MM + j];
+        // software-pipelined: column l + 1 is updated first and the reciprocal of its pivot is started before the
+        // updates of the columns behind it, so the 72-cycle reciprocal overlaps with them
+        if (!(ALTRO_TRI(0, 0) > 0.0)) return true;  // (the same value in every lane)
+        rr[0] = __drcp_rn(ALTRO_TRI(0, 0));
 #pragma unroll
-        for (int l = 0; l < MM; ++l) {
-            if (!(ALTRO_TRI(l, l) > 0.0)) return true;  // the same value in every lane
-            rr[l] = __drcp_rn(ALTRO_TRI(l, l));
+        for (int l = 0; l < MM - 1; ++l) {
+            {
+                const int j = l + 1;
+                const double t = ALTRO_TRI(j, l) * rr[l];
 #pragma unroll
-            for (int j = l + 1; j < MM; ++j) {
+                for (int i = j; i < MM; ++i) ALTRO_TRI(i, j) = fma(-ALTRO_TRI(i, l), t, ALTRO_TRI(i, j));
+            }
+            if (!(ALTRO_TRI(l + 1, l + 1) > 0.0)) return true;
+            rr[l + 1] = __drcp_rn(ALTRO_TRI(l + 1, l + 1));
+#pragma unroll
+            for (int j = l + 2; j < MM; ++j) {
                 const double t = ALTRO_TRI(j, l) * rr[l];
 #pragma unroll
                 for (int i = j; i < MM; ++i) ALTRO_TRI(i, j) = fma(-ALTRO_TRI(i, l), t, ALTRO_TRI(i, j));
@@ -292,22 +302,24 @@ __device__ __noinline__ bool ldl_solve_medium(double *L, const double *Qux, cons
             double *bp = (c < n) ? Kk + c : dk_;
             const double *src = (c < n) ? Qux + c : Qu;
             const int st = (c < n) ? n : 1;
-            double bb[MM];
+            // column-oriented in time, row chains in value: entry i still accumulates over ascending (forward) /
+            // descending (backward) l, but once bb[l] is final all the entries behind it take one independent fma each
+            double bb[MM], a2[MM];
 #pragma unroll
-            for (int i = 0; i < MM; ++i) {
-                double acc = -src[i * st];
+            for (int i = 0; i < MM; ++i) bb[i] = -src[i * st];
 #pragma unroll
-                for (int l = 0; l < i; ++l) acc = fma(-ALTRO_TRI(i, l), bb[l] * rr[l], acc);
-                bb[i] = acc;
+            for (int l = 0; l < MM - 1; ++l) {
+                const double t = bb[l] * rr[l];
+#pragma unroll
+                for (int i = l + 1; i < MM; ++i) bb[i] = fma(-ALTRO_TRI(i, l), t, bb[i]);
             }
 #pragma unroll
-            for (int i = 0; i < MM; ++i) bb[i] = bb[i] * rr[i];
+            for (int i = 0; i < MM; ++i) { bb[i] = bb[i] * rr[i]; a2[i] = 0.0; }
 #pragma unroll
-            for (int i = MM - 1; i >= 0; --i) {
-                double acc2 = 0.0;
+            for (int l = MM - 1; l >= 0; --l) {
+                bb[l] = fma(-rr[l], a2[l], bb[l]);
 #pragma unroll
-                for (int l = MM - 1; l > i; --l) acc2 = fma(ALTRO_TRI(l, i), bb[l], acc2);
-                bb[i] = fma(-rr[i], acc2, bb[i]);
+                for (int i = l - 1; i >= 0; --i) a2[i] = fma(ALTRO_TRI(l, i), bb[l], a2[i]);
             }
 #pragma unroll
             for (int i = 0; i < MM; ++i) bp[i * st] = bb[i];
