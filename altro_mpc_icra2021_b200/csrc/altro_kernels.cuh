@@ -1252,6 +1252,34 @@ struct Ctx {
         }
     }
 
+    // Two tiles interleaved: the chains of tile 0 and tile 1 are independent, so issuing their k-steps alternately hides
+    // the shared-memory and DMMA latency of one behind the other (a single chain is LDS -> DMMA -> LDS -> DMMA ...,
+    // about 60 cycles per k-step with nothing else to issue).  Each chain is unchanged.  `two` is warp-uniform; the
+    // operand functors take the slot (0 / 1) first and must be safe to evaluate for slot 1 even when it is unused.
+    template <class FA, class FB>
+    __device__ __forceinline__ void mma_chain2(double (&c)[2][2], bool two, int K, FA a_at, FB b_at) const
+    {
+        const int lane = tid & 31, r = lane >> 2, q = lane & 3;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            const double a0 = a_at(0, r, k0 + q), b0 = b_at(0, k0 + q, r);
+            const double a1 = a_at(1, r, k0 + q), b1 = b_at(1, k0 + q, r);
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[0][0]), "+d"(c[0][1]) : "d"(a0), "d"(b0));
+            if (two)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[1][0]), "+d"(c[1][1]) : "d"(a1), "d"(b1));
+        }
+    }
+    // The tiles of one product, dealt to the warps round-robin continuing a running tile index `goff` (so that products
+    // with a single tile do not all land on warp 0), two of a warp's tiles at a time.  body(t0, t1, two).
+    template <class F>
+    __device__ __forceinline__ void tile_pairs(int nt, int goff, F body) const
+    {
+        constexpr int NW = T / 32;
+        const int warp = tid >> 5;
+        for (int t = (warp + NW - goff % NW) % NW; t < nt; t += 2 * NW) body(t, t + NW < nt ? t + NW : t, t + NW < nt);
+    }
+
     // Register-blocked tile GEMM for the large-dimension path:  C(i,j) = init(i,j) + sum_l a1(i,l) b1(l,j)
     // [+ sum_l a2(i,l) b2(l,j)], every chain over ascending l exactly like mma_chain.  A warp owns a 16 x 32 block of C
     // (2 x 4 DMMA tiles: two A and four B fragments feed eight independent accumulator chains per k-step), the
@@ -1408,29 +1436,38 @@ struct Ctx {
                               [&](int l, int j) { return (l < n && j < m) ? Bm[l * m + j] : 0.0; }, 0, zero_a, zero_a,
                               [&](int i, int j, double v) { if (i < n && j < m) SB[i * m + j] = v; });
                 }
-                for (int t = warp; !big && t < tn * (tn + tm); t += NW) {
-                    const int r0 = (t / (tn + tm)) << 3, ct = t % (tn + tm);
-                    const int i = r0 + fr;
-                    double d0 = 0.0, d1 = 0.0;
-                    if (ct < tn) {
-                        const int c0 = ct << 3, j = c0 + fc;
-                        mma_chain(d0, d1, n,
-                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
-                                  [&](int l, int jj) { jj += c0; return (l < n && jj < n) ? A[l * n + jj] : 0.0; });
-                        if (i < n) {
-                            if (j < n) SA[i * n + j] = d0;
-                            if (j + 1 < n) SA[i * n + j + 1] = d1;
+                if (!big) {
+                    // SA = S A (tn x tn tiles), then SB = S B (tn x tm tiles)
+                    tile_pairs(tn * tn, 0, [&](int t0, int t1, bool two) {
+                        const int r0[2] = {(t0 / tn) << 3, (t1 / tn) << 3}, c0[2] = {(t0 % tn) << 3, (t1 % tn) << 3};
+                        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                        mma_chain2(c, two, n,
+                                   [&](int u, int ii, int l) { ii += r0[u]; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
+                                   [&](int u, int l, int jj) { jj += c0[u]; return (l < n && jj < n) ? A[l * n + jj] : 0.0; });
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = r0[u] + fr, j = c0[u] + fc;
+                            if ((u == 0 || two) && i < n) {
+                                if (j < n) SA[i * n + j] = c[u][0];
+                                if (j + 1 < n) SA[i * n + j + 1] = c[u][1];
+                            }
                         }
-                    } else {
-                        const int c0 = (ct - tn) << 3, j = c0 + fc;
-                        mma_chain(d0, d1, n,
-                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
-                                  [&](int l, int jj) { jj += c0; return (l < n && jj < m) ? Bm[l * m + jj] : 0.0; });
-                        if (i < n) {
-                            if (j < m) SB[i * m + j] = d0;
-                            if (j + 1 < m) SB[i * m + j + 1] = d1;
+                    });
+                    tile_pairs(tn * tm, tn * tn, [&](int t0, int t1, bool two) {
+                        const int r0[2] = {(t0 / tm) << 3, (t1 / tm) << 3}, c0[2] = {(t0 % tm) << 3, (t1 % tm) << 3};
+                        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                        mma_chain2(c, two, n,
+                                   [&](int u, int ii, int l) { ii += r0[u]; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
+                                   [&](int u, int l, int jj) { jj += c0[u]; return (l < n && jj < m) ? Bm[l * m + jj] : 0.0; });
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = r0[u] + fr, j = c0[u] + fc;
+                            if ((u == 0 || two) && i < n) {
+                                if (j < m) SB[i * m + j] = c[u][0];
+                                if (j + 1 < m) SB[i * m + j + 1] = c[u][1];
+                            }
                         }
-                    }
+                    });
                 }
                 gsync<T>();
                 ALTRO_TICK(0);
@@ -1481,53 +1518,74 @@ struct Ctx {
                                   }
                               });
                 }
-                for (int t = warp; !big && t < nt_xx + nt_ux + nt_uu; t += NW) {
-                    if (t < nt_xx) {
-                        const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
-                        const int i = r0 + fr, j = c0 + fc;
-                        double d0 = (i < n) ? (j < n ? Qi[oQxx + i * n + j] : (j == n ? Qi[i] : 0.0)) : 0.0;
-                        double d1 = (i < n) ? (j + 1 < n ? Qi[oQxx + i * n + j + 1] : (j + 1 == n ? Qi[i] : 0.0)) : 0.0;
-                        mma_chain(d0, d1, n,
-                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? A[l * n + ii] : 0.0; },
-                                  [&](int l, int jj) {
-                                      jj += c0;
-                                      const double *p = jj < n ? SA + l * n + jj : s + l;
-                                      return (l < n && jj <= n) ? *p : 0.0;
-                                  });
-                        if (i < n) {
-                            if (j < n) Qxx[i * n + j] = d0; else if (j == n) Qx[i] = d0;
-                            if (j + 1 < n) Qxx[i * n + j + 1] = d1; else if (j + 1 == n) Qx[i] = d1;
+                if (!big) {
+                    tile_pairs(nt_xx, 0, [&](int t0, int t1, bool two) {
+                        const int r0[2] = {(t0 / tn1) << 3, (t1 / tn1) << 3}, c0[2] = {(t0 % tn1) << 3, (t1 % tn1) << 3};
+                        double c[2][2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = r0[u] + fr, j = c0[u] + fc;
+                            c[u][0] = (i < n) ? (j < n ? Qi[oQxx + i * n + j] : (j == n ? Qi[i] : 0.0)) : 0.0;
+                            c[u][1] = (i < n) ? (j + 1 < n ? Qi[oQxx + i * n + j + 1] : (j + 1 == n ? Qi[i] : 0.0)) : 0.0;
                         }
-                    } else if (t < nt_xx + nt_ux) {
-                        const int u = t - nt_xx, r0 = (u / tn) << 3, c0 = (u % tn) << 3;
-                        const int i = r0 + fr, j = c0 + fc;
-                        double d0 = 0.0, d1 = 0.0;
-                        mma_chain(d0, d1, n,
-                                  [&](int ii, int l) { ii += r0; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
-                                  [&](int l, int jj) { jj += c0; return (l < n && jj < n) ? SA[l * n + jj] : 0.0; });
-                        if (i < m) {
-                            if (j < n) Qux[i * n + j] = d0;
-                            if (j + 1 < n) Qux[i * n + j + 1] = d1;
+                        mma_chain2(c, two, n,
+                                   [&](int u, int ii, int l) { ii += r0[u]; return (ii < n && l < n) ? A[l * n + ii] : 0.0; },
+                                   [&](int u, int l, int jj) {
+                                       jj += c0[u];
+                                       const double *p = jj < n ? SA + l * n + jj : s + l;
+                                       return (l < n && jj <= n) ? *p : 0.0;
+                                   });
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = r0[u] + fr, j = c0[u] + fc;
+                            if ((u == 0 || two) && i < n) {
+                                if (j < n) Qxx[i * n + j] = c[u][0]; else if (j == n) Qx[i] = c[u][0];
+                                if (j + 1 < n) Qxx[i * n + j + 1] = c[u][1]; else if (j + 1 == n) Qx[i] = c[u][1];
+                            }
                         }
-                    } else {
-                        const int u = t - nt_xx - nt_ux, r0 = (u / tm1) << 3, c0 = (u % tm1) << 3;
-                        const int i = r0 + fr, j = c0 + fc;
-                        double d0 = (i < m) ? (j < m ? Qi[oQuu + i * m + j] : (j == m ? Qi[oQu + i] : 0.0)) : 0.0;
-                        double d1 = (i < m) ? (j + 1 < m ? Qi[oQuu + i * m + j + 1] : (j + 1 == m ? Qi[oQu + i] : 0.0)) : 0.0;
-                        mma_chain(d0, d1, n,
-                                  [&](int ii, int l) { ii += r0; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
-                                  [&](int l, int jj) {
-                                      jj += c0;
-                                      const double *p = jj < m ? SB + l * m + jj : s + l;
-                                      return (l < n && jj <= m) ? *p : 0.0;
-                                  });
-                        if (i < m) {  // L = Quu + rho I: regularised copy for the factorisation
-                            if (j < m) { Quu[i * m + j] = d0; L[i * m + j] = d0 + ((i == j) ? rho : 0.0); }
-                            else if (j == m) Qu[i] = d0;
-                            if (j + 1 < m) { Quu[i * m + j + 1] = d1; L[i * m + j + 1] = d1 + ((i == j + 1) ? rho : 0.0); }
-                            else if (j + 1 == m) Qu[i] = d1;
+                    });
+                    tile_pairs(nt_ux, nt_xx, [&](int t0, int t1, bool two) {
+                        const int r0[2] = {(t0 / tn) << 3, (t1 / tn) << 3}, c0[2] = {(t0 % tn) << 3, (t1 % tn) << 3};
+                        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                        mma_chain2(c, two, n,
+                                   [&](int u, int ii, int l) { ii += r0[u]; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
+                                   [&](int u, int l, int jj) { jj += c0[u]; return (l < n && jj < n) ? SA[l * n + jj] : 0.0; });
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = r0[u] + fr, j = c0[u] + fc;
+                            if ((u == 0 || two) && i < m) {
+                                if (j < n) Qux[i * n + j] = c[u][0];
+                                if (j + 1 < n) Qux[i * n + j + 1] = c[u][1];
+                            }
                         }
-                    }
+                    });
+                    tile_pairs(nt_uu, nt_xx + nt_ux, [&](int t0, int t1, bool two) {
+                        const int r0[2] = {(t0 / tm1) << 3, (t1 / tm1) << 3}, c0[2] = {(t0 % tm1) << 3, (t1 % tm1) << 3};
+                        double c[2][2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = r0[u] + fr, j = c0[u] + fc;
+                            c[u][0] = (i < m) ? (j < m ? Qi[oQuu + i * m + j] : (j == m ? Qi[oQu + i] : 0.0)) : 0.0;
+                            c[u][1] = (i < m) ? (j + 1 < m ? Qi[oQuu + i * m + j + 1] : (j + 1 == m ? Qi[oQu + i] : 0.0)) : 0.0;
+                        }
+                        mma_chain2(c, two, n,
+                                   [&](int u, int ii, int l) { ii += r0[u]; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
+                                   [&](int u, int l, int jj) {
+                                       jj += c0[u];
+                                       const double *p = jj < m ? SB + l * m + jj : s + l;
+                                       return (l < n && jj <= m) ? *p : 0.0;
+                                   });
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = r0[u] + fr, j = c0[u] + fc;
+                            if ((u == 0 || two) && i < m) {  // L = Quu + rho I: regularised copy for the factorisation
+                                if (j < m) { Quu[i * m + j] = c[u][0]; L[i * m + j] = c[u][0] + ((i == j) ? rho : 0.0); }
+                                else if (j == m) Qu[i] = c[u][0];
+                                if (j + 1 < m) { Quu[i * m + j + 1] = c[u][1]; L[i * m + j + 1] = c[u][1] + ((i == j + 1) ? rho : 0.0); }
+                                else if (j + 1 == m) Qu[i] = c[u][1];
+                            }
+                        }
+                    });
                 }
                 gsync<T>();
                 ALTRO_TICK(2);
