@@ -1436,7 +1436,7 @@ struct Ctx {
                               [&](int l, int j) { return (l < n && j < m) ? Bm[l * m + j] : 0.0; }, 0, zero_a, zero_a,
                               [&](int i, int j, double v) { if (i < n && j < m) SB[i * m + j] = v; });
                 }
-                if (!big) {
+                if constexpr (NX > 0) {  // compiled dimensions: two tiles of a product interleaved per warp
                     // SA = S A (tn x tn tiles), then SB = S B (tn x tm tiles)
                     tile_pairs(tn * tn, 0, [&](int t0, int t1, bool two) {
                         const int r0[2] = {(t0 / tn) << 3, (t1 / tn) << 3}, c0[2] = {(t0 % tn) << 3, (t1 % tn) << 3};
@@ -1468,6 +1468,32 @@ struct Ctx {
                             }
                         }
                     });
+                } else {
+                // run-time dimensions: one tile at a time (measured: the interleaved form costs this kernel 10 % at small n)
+                for (int t = warp; !big && t < tn * (tn + tm); t += NW) {
+                    const int r0 = (t / (tn + tm)) << 3, ct = t % (tn + tm);
+                    const int i = r0 + fr;
+                    double d0 = 0.0, d1 = 0.0;
+                    if (ct < tn) {
+                        const int c0 = ct << 3, j = c0 + fc;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
+                                  [&](int l, int jj) { jj += c0; return (l < n && jj < n) ? A[l * n + jj] : 0.0; });
+                        if (i < n) {
+                            if (j < n) SA[i * n + j] = d0;
+                            if (j + 1 < n) SA[i * n + j + 1] = d1;
+                        }
+                    } else {
+                        const int c0 = (ct - tn) << 3, j = c0 + fc;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? S[ii * n + l] : 0.0; },
+                                  [&](int l, int jj) { jj += c0; return (l < n && jj < m) ? Bm[l * m + jj] : 0.0; });
+                        if (i < n) {
+                            if (j < m) SB[i * m + j] = d0;
+                            if (j + 1 < m) SB[i * m + j + 1] = d1;
+                        }
+                    }
+                }
                 }
                 gsync<T>();
                 ALTRO_TICK(0);
@@ -1518,7 +1544,7 @@ struct Ctx {
                                   }
                               });
                 }
-                if (!big) {
+                if constexpr (NX > 0) {
                     tile_pairs(nt_xx, 0, [&](int t0, int t1, bool two) {
                         const int r0[2] = {(t0 / tn1) << 3, (t1 / tn1) << 3}, c0[2] = {(t0 % tn1) << 3, (t1 % tn1) << 3};
                         double c[2][2];
@@ -1586,6 +1612,55 @@ struct Ctx {
                             }
                         }
                     });
+                } else {
+                for (int t = warp; !big && t < nt_xx + nt_ux + nt_uu; t += NW) {
+                    if (t < nt_xx) {
+                        const int r0 = (t / tn1) << 3, c0 = (t % tn1) << 3;
+                        const int i = r0 + fr, j = c0 + fc;
+                        double d0 = (i < n) ? (j < n ? Qi[oQxx + i * n + j] : (j == n ? Qi[i] : 0.0)) : 0.0;
+                        double d1 = (i < n) ? (j + 1 < n ? Qi[oQxx + i * n + j + 1] : (j + 1 == n ? Qi[i] : 0.0)) : 0.0;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < n && l < n) ? A[l * n + ii] : 0.0; },
+                                  [&](int l, int jj) {
+                                      jj += c0;
+                                      const double *p = jj < n ? SA + l * n + jj : s + l;
+                                      return (l < n && jj <= n) ? *p : 0.0;
+                                  });
+                        if (i < n) {
+                            if (j < n) Qxx[i * n + j] = d0; else if (j == n) Qx[i] = d0;
+                            if (j + 1 < n) Qxx[i * n + j + 1] = d1; else if (j + 1 == n) Qx[i] = d1;
+                        }
+                    } else if (t < nt_xx + nt_ux) {
+                        const int u = t - nt_xx, r0 = (u / tn) << 3, c0 = (u % tn) << 3;
+                        const int i = r0 + fr, j = c0 + fc;
+                        double d0 = 0.0, d1 = 0.0;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
+                                  [&](int l, int jj) { jj += c0; return (l < n && jj < n) ? SA[l * n + jj] : 0.0; });
+                        if (i < m) {
+                            if (j < n) Qux[i * n + j] = d0;
+                            if (j + 1 < n) Qux[i * n + j + 1] = d1;
+                        }
+                    } else {
+                        const int u = t - nt_xx - nt_ux, r0 = (u / tm1) << 3, c0 = (u % tm1) << 3;
+                        const int i = r0 + fr, j = c0 + fc;
+                        double d0 = (i < m) ? (j < m ? Qi[oQuu + i * m + j] : (j == m ? Qi[oQu + i] : 0.0)) : 0.0;
+                        double d1 = (i < m) ? (j + 1 < m ? Qi[oQuu + i * m + j + 1] : (j + 1 == m ? Qi[oQu + i] : 0.0)) : 0.0;
+                        mma_chain(d0, d1, n,
+                                  [&](int ii, int l) { ii += r0; return (ii < m && l < n) ? Bm[l * m + ii] : 0.0; },
+                                  [&](int l, int jj) {
+                                      jj += c0;
+                                      const double *p = jj < m ? SB + l * m + jj : s + l;
+                                      return (l < n && jj <= m) ? *p : 0.0;
+                                  });
+                        if (i < m) {  // L = Quu + rho I: regularised copy for the factorisation
+                            if (j < m) { Quu[i * m + j] = d0; L[i * m + j] = d0 + ((i == j) ? rho : 0.0); }
+                            else if (j == m) Qu[i] = d0;
+                            if (j + 1 < m) { Quu[i * m + j + 1] = d1; L[i * m + j + 1] = d1 + ((i == j + 1) ? rho : 0.0); }
+                            else if (j + 1 == m) Qu[i] = d1;
+                        }
+                    }
+                }
                 }
                 gsync<T>();
                 ALTRO_TICK(2);
