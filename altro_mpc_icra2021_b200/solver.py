@@ -160,8 +160,9 @@ class ALTROSolver:
 
     def close(self) -> None:
         if getattr(self, "h", None) and self.h.value:
-            for a in self._pinned:
+            for a in self._pinned + getattr(self, "_runbuf", []):
                 self.lib.altro_host_unregister(_p(a))
+            self._runbuf, self._runbuf_steps = [], 0
             self.lib.altro_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -321,20 +322,40 @@ class ALTROSolver:
         self._ck(self.lib.altro_mpc_transition(self.h, _p(nz), int(shift)))
         self.prob.kidx += 1
 
-    def mpc_run(self, steps: int, shift: bool = True, fetch: bool = True):
+    def mpc_run(self, steps: int, shift: bool = True, fetch: bool = True, reuse_buffers: bool = False):
         """Closed-loop MPC run on the device: `steps` x {transition; solve!} per instance in one launch.
         Returns a dict of per-step results (see altro_mpc_run) when fetch=True."""
         self.upload()
         self._ck(self.lib.altro_mpc_run(self.h, int(steps), int(shift)))
         self.prob.kidx += int(steps)  # host mirror of the timeline positions the device just advanced
         self._results_stale = True
-        return self.run_results(steps) if fetch else None
+        return self.run_results(steps, reuse_buffers) if fetch else None
 
-    def run_results(self, steps: int) -> dict:
+    def _run_buffers(self, steps: int, reuse: bool):
+        """Host arrays the run results are copied into.  reuse=True hands out views of one page-locked set kept by
+        the solver (valid until the next call with reuse=True): what a caller that reads results every control tick
+        does -- fresh pageable arrays cost page faults and a staged copy on every call."""
         p, B = self.prob, self.prob.B
-        it, ito, st, ls = (np.zeros((steps, B), np.int32) for _ in range(4))
-        cost, cmax = np.zeros((steps, B)), np.zeros((steps, B))
-        x0l, u0l, tns = np.zeros((steps, B, p.n)), np.zeros((steps, B, p.m)), np.zeros((steps, B), np.int64)
+        shapes = [((B,), np.int32)] * 4 + [((B,), np.float64)] * 2 + [((B, p.n), np.float64), ((B, p.m), np.float64),
+                                                                      ((B,), np.int64)]
+        if not reuse:
+            return [np.zeros((steps,) + sh, dt) for sh, dt in shapes]
+        if getattr(self, "_runbuf_steps", 0) < steps:
+            for a in getattr(self, "_runbuf", []):
+                self.lib.altro_host_unregister(_p(a))
+            self._runbuf = [np.zeros((steps,) + sh, dt) for sh, dt in shapes]
+            for a in self._runbuf:
+                self.lib.altro_host_register(_p(a), C.c_size_t(a.nbytes))  # best effort: pageable still works
+            self._runbuf_steps = steps
+        return [a[:steps] for a in self._runbuf]
+
+    def reserve_host_results(self, steps: int) -> None:
+        """Allocates and page-locks the reusable result buffers of run_results(..., reuse_buffers=True) ahead of time."""
+        self._run_buffers(steps, True)
+
+    def run_results(self, steps: int, reuse_buffers: bool = False) -> dict:
+        p = self.prob
+        it, ito, st, ls, cost, cmax, x0l, u0l, tns = self._run_buffers(steps, reuse_buffers)
         self._ck(self.lib.altro_get_run_results(self.h, steps, _p(it), _p(ito), _p(st), _p(ls), _p(cost), _p(cmax),
                                                 _p(x0l), _p(u0l), _p(tns)))
         self._ck(self.lib.altro_get_trajectory(self.h, _p(p.X), _p(p.U)))

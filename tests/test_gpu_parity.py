@@ -174,6 +174,31 @@ def test_repeated_runs_are_identical_and_logs_survive_reallocation():
     assert np.abs(runs[0]["u0"]).max() > 0
 
 
+def test_reusable_page_locked_result_buffers_return_the_same_results():
+    """run_results(reuse_buffers=True) copies into one page-locked set kept by the solver (what a caller that reads
+    results every tick does): same numbers as the fresh-array path, views valid until the next reuse call."""
+    cold = np.load(os.path.join(GOLD, "rocket_cold.npz"))
+    B = 48
+    ks = mpc.rng_for(5, 1).integers(0, cold["X"].shape[0] - 21 - 40, size=B)
+    noise = mpc.rng_for(4, 4).standard_normal((6, B, 6))
+    prob, opts, _, _ = cases.case_rocket_mpc(cold["X"], cold["U"], batch=B)
+    sv = gpu_solver(prob, opts, pin=True).solve()
+    sv.set_track(cold["X"], cold["U"], ks)
+    sv.set_noise_model(2, 1e-3, 1e-2)
+    sv.set_noise_bank(noise)
+    sv.snapshot()
+    fresh = sv.mpc_run(6)
+    sv.restore()
+    sv.reserve_host_results(6)
+    again = sv.mpc_run(6, reuse_buffers=True)
+    for k in ("iterations", "ls_trials", "status", "cost", "c_max", "x0", "u0"):
+        assert np.array_equal(fresh[k], again[k]), k
+    sv.restore()
+    short = sv.mpc_run(2, reuse_buffers=True)  # a shorter run reuses the same buffers
+    assert short["x0"].shape[0] == 2 and np.array_equal(short["x0"], fresh["x0"][:2])
+    sv.close()
+
+
 def test_runtime_dimension_kernel_matches_compiled_dimensions(monkeypatch):
     prob, opts, _, _ = cases.case_random_linear(batch=8)
     ref = copy.deepcopy(prob)
